@@ -48,7 +48,8 @@ class RngState(C.Structure):
 
 
 class CdParams(C.Structure):
-    _fields_ = [("num_iters", C.c_int32), ("viol_tol", C.c_double), ("tol", C.c_double), ("phase1", C.c_int32), ("fast", C.c_int32)]
+    _fields_ = [("num_iters", C.c_int32), ("viol_tol", C.c_double), ("tol", C.c_double), ("phase1", C.c_int32), ("fast", C.c_int32),
+                ("refresh_every", C.c_int32)]
 
 
 class CdStats(C.Structure):
@@ -186,10 +187,10 @@ class Problem:
         return tuple(out)
 
     # -- coordinate descent -----------------------------------------------------------------
-    def improve_cd(self, x0, rng, num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, fast=False, only_phase=None):
+    def improve_cd(self, x0, rng, num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, fast=False, only_phase=None, refresh_every=0):
         """improve_coord_descent (qcqp.py:181-192). rng: RngState (advanced in place). Returns (x, CdStats)."""
         x = np.array(x0, dtype=np.float64, copy=True)
-        prm = CdParams(num_iters, viol_tol, tol, int(bool(phase1)), int(bool(fast)))
+        prm = CdParams(num_iters, viol_tol, tol, int(bool(phase1)), int(bool(fast)), int(refresh_every))
         st = CdStats()
         if only_phase is None:
             lib().orc_improve_cd(self.h, C.byref(prm), _ptr(x), C.byref(rng), C.byref(st))
@@ -197,10 +198,10 @@ class Problem:
             lib().orc_cd_phase(self.h, C.byref(prm), int(only_phase), _ptr(x), C.byref(rng), C.byref(st))
         return x, st
 
-    def improve_cd_batch(self, X0, rngs, num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, fast=False, nthreads=0):
+    def improve_cd_batch(self, X0, rngs, num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, fast=False, nthreads=0, refresh_every=0):
         X = np.array(X0, dtype=np.float64, copy=True).reshape(-1, self.n)
         R = X.shape[0]
-        prm = CdParams(num_iters, viol_tol, tol, int(bool(phase1)), int(bool(fast)))
+        prm = CdParams(num_iters, viol_tol, tol, int(bool(phase1)), int(bool(fast)), int(refresh_every))
         st = (CdStats * R)()
         f0 = np.empty(R); mv = np.empty(R)
         lib().orc_improve_cd_batch(self.h, C.byref(prm), R, _ptr(X), C.byref(rngs), _ptr(f0), _ptr(mv), C.byref(st), nthreads)

@@ -525,6 +525,7 @@ typedef struct {
     double tol;          /* 1e-4 */
     int32_t phase1;      /* 1 */
     int32_t fast;        /* 0 faithful, 1 cached-f/incidence-list */
+    int32_t refresh_every; /* fast mode: recompute the cached f_j every this many phase-2 sweeps (0 = 64) */
 } orc_cd_params;
 
 typedef struct {
@@ -676,7 +677,10 @@ static void cd_phase2(cd_ctx* c, const orc_problem* p, double* x, const orc_cd_p
                 if (update_counter == n) { converged = 1; break; }
             }
         }
-        if (prm->fast && !converged) refresh_fval(c, p, x);
+        if (prm->fast && !converged) {
+            int every = prm->refresh_every > 0 ? prm->refresh_every : 64;
+            if ((t + 1) % every == 0) refresh_fval(c, p, x);
+        }
     }
 }
 

@@ -1,0 +1,195 @@
+// api.cu -- extern "C" entry points of libqcqp_b200.so (include/qcqp_b200.h).  Host-buffer variants stage through
+// device memory and synchronise; _device variants only enqueue on the caller's stream.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace qcqp {
+int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0,
+              double* dmv, qcqp_cd_stats* dstats, cudaStream_t stream);
+int eval_launch(qcqp_pack* p, const double* dX, int R, double* df0, double* dmv, double* dviol, cudaStream_t stream);
+int best_launch(const double* df0, const double* dmv, int R, double tol, int* dbest, long long* dbucket, double* dbf, cudaStream_t stream);
+int admm_launch(qcqp_pack* p, const qcqp_admm_params* prm, const double* drhos, const double* dZinv, int K, const double* dX0, int R,
+                double* dX, double* df0, double* dmv, qcqp_admm_stats* dstats, cudaStream_t stream);
+int sdr_launch(qcqp_pack* p, const double* dmu, const double* dF, const double* dZ, uint64_t seed, int S, double* dX, double* df0,
+               double* dmv, cudaStream_t stream);
+
+// scoped device buffers for the host-buffer entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes)
+    {
+        cudaError_t e = cudaMalloc(&p, bytes > 0 ? bytes : 1);
+        if (e != cudaSuccess) { p = nullptr; return fail(QCQP_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+        return QCQP_OK;
+    }
+    template <class T> T* as() { return (T*)p; }
+};
+
+static int check_pack(qcqp_pack* p, const char* who)
+{
+    if (!p) return fail(QCQP_ERR_INVALID, std::string(who) + ": null pack");
+    cudaError_t e = cudaSetDevice(p->device);
+    if (e != cudaSuccess) return fail(QCQP_ERR_CUDA, std::string(who) + ": cudaSetDevice: " + cudaGetErrorString(e));
+    return QCQP_OK;
+}
+}  // namespace qcqp
+
+using namespace qcqp;
+
+#define TRY(x) do { int rc__ = (x); if (rc__ != QCQP_OK) return rc__; } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qcqp_eval_device(qcqp_pack* pack, const double* dX, int32_t R, double* df0, double* dmaxviol, double* dviol, void* stream)
+{
+    TRY(check_pack(pack, "qcqp_eval_device"));
+    if (R < 0 || (R > 0 && (!dX || !df0 || !dmaxviol))) return fail(QCQP_ERR_INVALID, "qcqp_eval_device: bad argument");
+    return eval_launch(pack, dX, R, df0, dmaxviol, dviol, (cudaStream_t)stream);
+}
+
+extern "C" int qcqp_eval(qcqp_pack* pack, const double* X, int32_t R, double* f0, double* maxviol, double* viol)
+{
+    TRY(check_pack(pack, "qcqp_eval"));
+    if (R < 0 || (R > 0 && (!X || !f0 || !maxviol))) return fail(QCQP_ERR_INVALID, "qcqp_eval: bad argument");
+    if (R == 0) return QCQP_OK;
+    const size_t n = pack->v.n, m = pack->v.m;
+    DevBuf dX, dF, dM, dV;
+    TRY(dX.alloc(R * n * 8)); TRY(dF.alloc(R * 8)); TRY(dM.alloc(R * 8));
+    if (viol) TRY(dV.alloc(R * m * 8));
+    QCQP_CUDA_TRY(cudaMemcpy(dX.p, X, R * n * 8, cudaMemcpyHostToDevice));
+    TRY(eval_launch(pack, dX.as<double>(), R, dF.as<double>(), dM.as<double>(), viol ? dV.as<double>() : nullptr, 0));
+    QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    QCQP_CUDA_TRY(cudaMemcpy(f0, dF.p, R * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(maxviol, dM.p, R * 8, cudaMemcpyDeviceToHost));
+    if (viol) QCQP_CUDA_TRY(cudaMemcpy(viol, dV.p, R * m * 8, cudaMemcpyDeviceToHost));
+    return QCQP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int check_cd_params(const qcqp_cd_params* p)
+{
+    if (!p) return fail(QCQP_ERR_INVALID, "qcqp_cd_improve: null params");
+    if (p->num_iters < 0) return fail(QCQP_ERR_INVALID, "qcqp_cd_improve: num_iters < 0");
+    return QCQP_OK;
+}
+
+extern "C" int qcqp_cd_improve_device(qcqp_pack* pack, const qcqp_cd_params* params, const double* dX0, int32_t R, qcqp_rng_state* drng,
+                                      double* dX, double* df0, double* dmaxviol, qcqp_cd_stats* dstats, void* stream)
+{
+    TRY(check_pack(pack, "qcqp_cd_improve_device"));
+    TRY(check_cd_params(params));
+    if (R < 0 || (R > 0 && (!dX0 || !drng || !dX || !df0 || !dmaxviol))) return fail(QCQP_ERR_INVALID, "qcqp_cd_improve_device: bad argument");
+    return cd_launch(pack, params, dX0, R, drng, dX, df0, dmaxviol, dstats, (cudaStream_t)stream);
+}
+
+extern "C" int qcqp_cd_improve(qcqp_pack* pack, const qcqp_cd_params* params, const double* X0, int32_t R, qcqp_rng_state* rng,
+                               double* X, double* f0, double* maxviol, qcqp_cd_stats* stats)
+{
+    TRY(check_pack(pack, "qcqp_cd_improve"));
+    TRY(check_cd_params(params));
+    if (R < 0 || (R > 0 && (!X0 || !rng || !X || !f0 || !maxviol))) return fail(QCQP_ERR_INVALID, "qcqp_cd_improve: bad argument");
+    if (R == 0) return QCQP_OK;
+    const size_t n = pack->v.n;
+    DevBuf dX0, dX, dF, dM, dR, dS;
+    TRY(dX0.alloc(R * n * 8)); TRY(dX.alloc(R * n * 8)); TRY(dF.alloc(R * 8)); TRY(dM.alloc(R * 8));
+    TRY(dR.alloc(R * sizeof(qcqp_rng_state))); TRY(dS.alloc(R * sizeof(qcqp_cd_stats)));
+    QCQP_CUDA_TRY(cudaMemcpy(dX0.p, X0, R * n * 8, cudaMemcpyHostToDevice));
+    QCQP_CUDA_TRY(cudaMemcpy(dR.p, rng, R * sizeof(qcqp_rng_state), cudaMemcpyHostToDevice));
+    TRY(cd_launch(pack, params, dX0.as<double>(), R, dR.as<qcqp_rng_state>(), dX.as<double>(), dF.as<double>(), dM.as<double>(),
+                  dS.as<qcqp_cd_stats>(), 0));
+    QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    QCQP_CUDA_TRY(cudaMemcpy(X, dX.p, R * n * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(f0, dF.p, R * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(maxviol, dM.p, R * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(rng, dR.p, R * sizeof(qcqp_rng_state), cudaMemcpyDeviceToHost));
+    if (stats) QCQP_CUDA_TRY(cudaMemcpy(stats, dS.p, R * sizeof(qcqp_cd_stats), cudaMemcpyDeviceToHost));
+    return QCQP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qcqp_admm_improve_device(qcqp_pack* pack, const qcqp_admm_params* params, const double* drhos, const double* dZinv,
+                                        int32_t K, const double* dX0, int32_t R, double* dX, double* df0, double* dmaxviol,
+                                        qcqp_admm_stats* dstats, void* stream)
+{
+    TRY(check_pack(pack, "qcqp_admm_improve_device"));
+    if (!params || K < 0 || R < 0) return fail(QCQP_ERR_INVALID, "qcqp_admm_improve_device: bad argument");
+    if (!pack->has_eig) return fail(QCQP_ERR_INVALID, "qcqp_admm_improve: call qcqp_admm_pack_eig first");
+    return admm_launch(pack, params, drhos, dZinv, K, dX0, R, dX, df0, dmaxviol, dstats, (cudaStream_t)stream);
+}
+
+extern "C" int qcqp_admm_improve(qcqp_pack* pack, const qcqp_admm_params* params, const double* rhos, const double* Zinv, int32_t K,
+                                 const double* X0, int32_t R, double* X, double* f0, double* maxviol, qcqp_admm_stats* stats)
+{
+    TRY(check_pack(pack, "qcqp_admm_improve"));
+    if (!params || K < 0 || R < 0 || !rhos || !Zinv || !X0 || !X || !f0 || !maxviol) return fail(QCQP_ERR_INVALID, "qcqp_admm_improve: bad argument");
+    if (!pack->has_eig) return fail(QCQP_ERR_INVALID, "qcqp_admm_improve: call qcqp_admm_pack_eig first");
+    if (K == 0 || R == 0) return QCQP_OK;
+    const size_t n = pack->v.n, KR = (size_t)K * R;
+    DevBuf dRho, dZ, dX0, dX, dF, dM, dS;
+    TRY(dRho.alloc(K * 8)); TRY(dZ.alloc(K * n * n * 8)); TRY(dX0.alloc(R * n * 8)); TRY(dX.alloc(KR * n * 8));
+    TRY(dF.alloc(KR * 8)); TRY(dM.alloc(KR * 8)); TRY(dS.alloc(KR * sizeof(qcqp_admm_stats)));
+    QCQP_CUDA_TRY(cudaMemcpy(dRho.p, rhos, K * 8, cudaMemcpyHostToDevice));
+    QCQP_CUDA_TRY(cudaMemcpy(dZ.p, Zinv, K * n * n * 8, cudaMemcpyHostToDevice));
+    QCQP_CUDA_TRY(cudaMemcpy(dX0.p, X0, R * n * 8, cudaMemcpyHostToDevice));
+    TRY(admm_launch(pack, params, dRho.as<double>(), dZ.as<double>(), K, dX0.as<double>(), R, dX.as<double>(), dF.as<double>(),
+                    dM.as<double>(), dS.as<qcqp_admm_stats>(), 0));
+    QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    QCQP_CUDA_TRY(cudaMemcpy(X, dX.p, KR * n * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(f0, dF.p, KR * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(maxviol, dM.p, KR * 8, cudaMemcpyDeviceToHost));
+    if (stats) QCQP_CUDA_TRY(cudaMemcpy(stats, dS.p, KR * sizeof(qcqp_admm_stats), cudaMemcpyDeviceToHost));
+    return QCQP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qcqp_sdr_sample_eval_device(qcqp_pack* pack, const double* dmu, const double* dF, const double* dZ, uint64_t seed, int32_t S,
+                                           double* dX, double* df0, double* dmaxviol, void* stream)
+{
+    TRY(check_pack(pack, "qcqp_sdr_sample_eval_device"));
+    if (S < 0 || (S > 0 && (!dmu || !dF || !dX || !df0 || !dmaxviol))) return fail(QCQP_ERR_INVALID, "qcqp_sdr_sample_eval_device: bad argument");
+    return sdr_launch(pack, dmu, dF, dZ, seed, S, dX, df0, dmaxviol, (cudaStream_t)stream);
+}
+
+extern "C" int qcqp_sdr_sample_eval(qcqp_pack* pack, const double* mu, const double* F, const double* Z, uint64_t seed, int32_t S,
+                                    double* X, double* f0, double* maxviol)
+{
+    TRY(check_pack(pack, "qcqp_sdr_sample_eval"));
+    if (S < 0 || (S > 0 && (!mu || !F || !X || !f0 || !maxviol))) return fail(QCQP_ERR_INVALID, "qcqp_sdr_sample_eval: bad argument");
+    if (S == 0) return QCQP_OK;
+    const size_t n = pack->v.n;
+    DevBuf dMu, dFm, dZ, dX, dF0, dM;
+    TRY(dMu.alloc(n * 8)); TRY(dFm.alloc(n * n * 8)); TRY(dX.alloc(S * n * 8)); TRY(dF0.alloc(S * 8)); TRY(dM.alloc(S * 8));
+    if (Z) { TRY(dZ.alloc(S * n * 8)); QCQP_CUDA_TRY(cudaMemcpy(dZ.p, Z, S * n * 8, cudaMemcpyHostToDevice)); }
+    QCQP_CUDA_TRY(cudaMemcpy(dMu.p, mu, n * 8, cudaMemcpyHostToDevice));
+    QCQP_CUDA_TRY(cudaMemcpy(dFm.p, F, n * n * 8, cudaMemcpyHostToDevice));
+    TRY(sdr_launch(pack, dMu.as<double>(), dFm.as<double>(), Z ? dZ.as<double>() : nullptr, seed, S, dX.as<double>(), dF0.as<double>(),
+                   dM.as<double>(), 0));
+    QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    QCQP_CUDA_TRY(cudaMemcpy(X, dX.p, S * n * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(f0, dF0.p, S * 8, cudaMemcpyDeviceToHost));
+    QCQP_CUDA_TRY(cudaMemcpy(maxviol, dM.p, S * 8, cudaMemcpyDeviceToHost));
+    return QCQP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qcqp_best_device(const double* df0, const double* dmaxviol, int32_t R, double tol, int32_t* dbest_idx, int64_t* dbest_bucket,
+                                double* dbest_f0, void* stream)
+{
+    if (R <= 0 || !df0 || !dmaxviol || !dbest_idx || !(tol > 0)) return fail(QCQP_ERR_INVALID, "qcqp_best_device: bad argument");
+    return best_launch(df0, dmaxviol, R, tol, dbest_idx, (long long*)dbest_bucket, dbest_f0, (cudaStream_t)stream);
+}
+
+extern "C" int qcqp_best(const double* f0, const double* maxviol, int32_t R, double tol, int32_t* best_idx)
+{
+    if (R <= 0 || !f0 || !maxviol || !best_idx || !(tol > 0)) return fail(QCQP_ERR_INVALID, "qcqp_best: bad argument");
+    if (qcqp_device_count() <= 0) return fail(QCQP_ERR_NO_DEVICE, "qcqp_best: no CUDA device visible; this engine has no CPU fallback");
+    DevBuf dF, dM, dI;
+    TRY(dF.alloc((size_t)R * 8)); TRY(dM.alloc((size_t)R * 8)); TRY(dI.alloc(4));
+    QCQP_CUDA_TRY(cudaMemcpy(dF.p, f0, (size_t)R * 8, cudaMemcpyHostToDevice));
+    QCQP_CUDA_TRY(cudaMemcpy(dM.p, maxviol, (size_t)R * 8, cudaMemcpyHostToDevice));
+    TRY(best_launch(dF.as<double>(), dM.as<double>(), R, tol, dI.as<int>(), nullptr, nullptr, 0));
+    QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    QCQP_CUDA_TRY(cudaMemcpy(best_idx, dI.p, 4, cudaMemcpyDeviceToHost));
+    return QCQP_OK;
+}

@@ -1,0 +1,575 @@
+// cd.cu -- two-phase coordinate descent for R independent restarts (improve_coord_descent, qcqp.py:181-192;
+// coord_descent_phase1 :101-148; coord_descent_phase2 :152-178; get_onevar_func utilities.py:99-105;
+// onevar_qcqp utilities.py:241-288).
+//
+// Mapping (DESIGN.md "CD sweep kernel"): ONE WARP PER RESTART.  A CTA holds W restart warps that walk the coordinates
+// k = 0..n-1 together, plus (when the problem has dense forms) one producer warp that streams row k of every dense
+// P_j from HBM/L2 into a shared-memory ring with cp.async.bulk (TMA unit) + mbarrier full/empty pairs, so a row is
+// fetched once per CTA and consumed by all W restarts.  Per restart, in shared memory: x[n], the cached f_j(x),
+// the MT19937 state, the one-variable coefficients of the forms incident to x_k, and the sweep-line events.
+// Per coordinate step a warp does: row dots (lanes over columns, shuffle reduction) -> (t2, t1, t0) per incident form
+// -> feasible set at level s (lanes over forms, fold + events) -> lane 0: sweep line + minimiser + RNG -> move and
+// incremental update f_j += ... of the incident forms.
+#include <cstdio>
+
+#include "common.cuh"
+#include "forms_eval.cuh"
+#include "onevar.cuh"
+
+namespace qcqp {
+
+constexpr int CD_LONG_ROW = 48;      // sparse rows longer than this are dotted by the whole warp (fast mode)
+constexpr int CD_SMALL_EVENTS = 40;  // up to this many events lane 0 insertion-sorts; beyond, warp bitonic sort
+
+struct CdLayout {
+    int W;            // restart warps per CTA
+    int S;            // ring stages (0: no dense forms)
+    int sc_cap;       // coefficient scratch entries in smem (0: global scratch)
+    int fval_smem;    // cached f_j in smem?
+    int evN;          // event capacity (power of two)
+    // byte offsets inside the dynamic smem block
+    unsigned off_bar, off_ring, off_warp0, warp_stride;
+    unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_evk, o_evd, o_clo, o_chi, o_dd, o_misc;
+    unsigned total;
+};
+
+struct CdK {
+    int num_iters;
+    double viol_tol, tol;
+    int phase1, strict, refresh_every;
+};
+
+struct WarpMem {
+    double* x;
+    double* fval;
+    uint32_t* mt;
+    double* scp; double* scq; double* scr; int* screl;
+    double* evk; int* evd;
+    double* clo; double* chi;
+    double* dd;       // dots of the dense rows of this step, by dense slot
+    int* misc;        // [0] event counter
+};
+
+enum { PH_P1 = 0, PH_P2 = 1, PH_DONE = 2 };
+
+// ---------------------------------------------------------------------------------------------------------
+// row dots
+// ---------------------------------------------------------------------------------------------------------
+// sparse row of incidence e against z = x with x_k := 0 (the stored row has no diagonal entry)
+__device__ __forceinline__ double sparse_row_dot_seq(const PackView& P, int e, const double* x)
+{
+    double s = 0.0;
+    for (int t = P.row_ptr[e]; t < P.row_ptr[e + 1]; t++) s = s + P.row_val[t] * x[P.row_col[t]];
+    return s;
+}
+__device__ __forceinline__ double sparse_row_dot_warp(const PackView& P, int e, const double* x, int lane)
+{
+    double s = 0.0;
+    for (int t = P.row_ptr[e] + lane; t < P.row_ptr[e + 1]; t += 32) s = fma(P.row_val[t], x[P.row_col[t]], s);
+    return warp_sum(s);
+}
+// dense row (length n, staged in smem or read from global) against z
+__device__ __forceinline__ double dense_row_dot_warp(const double* row, const double* x, int n, int k, int lane)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = lane;
+    for (; c + 96 < n; c += 128) {
+        s0 = fma(row[c], (c == k) ? 0.0 : x[c], s0);
+        s1 = fma(row[c + 32], (c + 32 == k) ? 0.0 : x[c + 32], s1);
+        s2 = fma(row[c + 64], (c + 64 == k) ? 0.0 : x[c + 64], s2);
+        s3 = fma(row[c + 96], (c + 96 == k) ? 0.0 : x[c + 96], s3);
+    }
+    for (; c < n; c += 32) s0 = fma(row[c], (c == k) ? 0.0 : x[c], s0);
+    return warp_sum((s0 + s1) + (s2 + s3));
+}
+__device__ __forceinline__ double dense_row_dot_seq(const double* row, const double* x, int n, int k)
+{
+    double s = 0.0;
+    for (int c = 0; c < n; c++) {
+        double v = row[c];
+        if (v != 0.0 && c != k) s = s + v * x[c];
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// warp-wide bitonic sort of (key, delta) pairs in shared memory; N is a power of two
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_events(double* key, int* del, int N, int lane)
+{
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < N; i += 32) {
+                int p = i ^ j;
+                if (p > i) {
+                    double a = key[i], b = key[p];
+                    bool up = ((i & k) == 0);
+                    if ((a > b) == up && a != b) {
+                        key[i] = b; key[p] = a;
+                        int t = del[i]; del[i] = del[p]; del[p] = t;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// onevar_qcqp(f0, nfs, s) for the mk constraint coefficients in scratch.  Warp-uniform return: 1 found / 0 None.
+// xout and err are valid in every lane; the RNG advances in lane 0 only.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int solve_level(const WarpMem& w, int mk, double s, double p0, double q0, double r0, MtRng& rng,
+                                           int evN, int lane, double* xout, int* err)
+{
+    Fold f;
+    f.init();
+    if (lane == 0) w.misc[0] = 0;
+    __syncwarp();
+    for (int i = lane; i < mk; i += 32) {
+        double p = w.scp[i], q = w.scq[i];
+        if (p == 0.0 && q == 0.0) continue;   // nfs filter of qcqp.py:116,166
+        f.mcnt++;
+        Ival I[2];
+        int c = feasible_intervals(p, q, w.scr[i], w.screl[i], s, I);
+        if (c == 0) f.nempty++;
+        else if (c == 1) f.add_single(I[0].lo, I[0].hi);
+        else {
+            int at = atomicAdd(&w.misc[0], 4);
+            w.evk[at] = I[0].lo; w.evd[at] = +1;
+            w.evk[at + 1] = I[0].hi; w.evd[at + 1] = -1;
+            w.evk[at + 2] = I[1].lo; w.evd[at + 2] = +1;
+            w.evk[at + 3] = I[1].hi; w.evd[at + 3] = -1;
+        }
+    }
+    if (mk > 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double L2 = __shfl_xor_sync(FULL, f.L, o), H2 = __shfl_xor_sync(FULL, f.H, o);
+            int mu2 = __shfl_xor_sync(FULL, f.mu, o), m12 = __shfl_xor_sync(FULL, f.m1, o);
+            int mc2 = __shfl_xor_sync(FULL, f.mcnt, o), ne2 = __shfl_xor_sync(FULL, f.nempty, o);
+            f.merge(L2, H2, mu2, m12, mc2, ne2);
+        }
+    } else {
+        f.L = bcast(f.L, 0); f.H = bcast(f.H, 0); f.mu = bcast_i(f.mu, 0); f.m1 = bcast_i(f.m1, 0);
+        f.mcnt = bcast_i(f.mcnt, 0); f.nempty = bcast_i(f.nempty, 0);
+    }
+    __syncwarp();
+    if (f.nempty > 0) return 0;   // some constraint has no feasible point at this level: the total never reaches m + 1
+    int nev = w.misc[0];
+    int found = 0, e = 0;
+    double xv = 0.0;
+    if (nev + 4 <= CD_SMALL_EVENTS) {
+        if (lane == 0) {
+            nev = finish_events(f, w.evk, w.evd, nev);
+            insertion_sort_events(w.evk, w.evd, nev);
+            int nC = sweep_sorted(w.evk, w.evd, nev, f.mcnt, w.clo, w.chi);
+            found = choose_point(p0, q0, r0, w.clo, w.chi, nC, rng, &xv, &e);
+        }
+    } else {
+        if (lane == 0) nev = finish_events(f, w.evk, w.evd, nev);
+        nev = bcast_i(nev, 0);
+        int N2 = 1;
+        while (N2 < nev) N2 <<= 1;
+        for (int i = nev + lane; i < N2; i += 32) { w.evk[i] = QCQP_INF; w.evd[i] = 0; }   // joins the +inf sentinel, adds 0
+        __syncwarp();
+        bitonic_sort_events(w.evk, w.evd, N2, lane);
+        if (lane == 0) {
+            int nC = sweep_sorted(w.evk, w.evd, N2, f.mcnt, w.clo, w.chi);
+            found = choose_point(p0, q0, r0, w.clo, w.chi, nC, rng, &xv, &e);
+        }
+    }
+    __syncwarp();
+    *xout = bcast(xv, 0);
+    *err = bcast_i(e, 0);
+    return bcast_i(found, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cached f_j(x) from scratch; returns max constraint violation (warp-uniform)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double refresh_fvals(const PackView& P, const WarpMem& w, int j0, bool strict, int lane)
+{
+    double* fv = w.fval;
+    eval_forms(P, w.x, j0, P.m, strict, lane, [&](int j, double v) { fv[j] = v; });
+    __syncwarp();
+    double mv = -QCQP_INF;
+    for (int j = 1 + lane; j <= P.m; j += 32) {
+        double v = violation_of(P.relop[j], fv[j]);
+        mv = (v > mv) ? v : mv;
+    }
+    return warp_max(mv);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+__global__ void cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __restrict__ X0, int R, qcqp_rng_state* rngs,
+                          double* __restrict__ X, double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out,
+                          double* ws_fval, double* ws_scr, int* ws_screl)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = P.n, m = P.m, nd = P.n_dense, ld = P.ld;
+    const int W = lay.W, S = lay.S;
+    const bool ring = (nd > 0);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
+    uint64_t* bar_empty = bar_full + (S > 0 ? S : 1);
+    double* ringbuf = reinterpret_cast<double*>(smem + lay.off_ring);
+    const unsigned row_bytes = (unsigned)ld * 8u;
+
+    if (ring && threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], W); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ================================= producer warp: stream dense rows =========================================
+    if (ring && warp == W) {
+        unsigned slot = 0;
+        for (;;) {
+            if (!__syncthreads_or(0)) break;   // pairs with the restart warps' vote at every sweep boundary
+            for (int k = 0; k < n; k++, slot++) {
+                int st = slot % S;
+                if (slot >= (unsigned)S) mbar_wait(&bar_empty[st], ((slot / S) + 1) & 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&bar_full[st], row_bytes * nd);
+                    for (int d = 0; d < nd; d++)
+                        bulk_g2s(ringbuf + ((size_t)st * nd + d) * ld, P.dense_P + ((size_t)d * n + k) * ld, row_bytes, &bar_full[st]);
+                }
+                __syncwarp();
+            }
+        }
+        return;
+    }
+
+    // ================================= restart warps ==============================================================
+    const int restart = blockIdx.x * W + warp;
+    const bool live = restart < R;
+    unsigned char* wb = smem + lay.off_warp0 + (size_t)warp * lay.warp_stride;
+    WarpMem w;
+    w.x = reinterpret_cast<double*>(wb + lay.o_x);
+    w.mt = reinterpret_cast<uint32_t*>(wb + lay.o_mt);
+    w.evk = reinterpret_cast<double*>(wb + lay.o_evk);
+    w.evd = reinterpret_cast<int*>(wb + lay.o_evd);
+    w.clo = reinterpret_cast<double*>(wb + lay.o_clo);
+    w.chi = reinterpret_cast<double*>(wb + lay.o_chi);
+    w.dd = reinterpret_cast<double*>(wb + lay.o_dd);
+    w.misc = reinterpret_cast<int*>(wb + lay.o_misc);
+    const size_t rr = live ? (size_t)restart : 0;
+    w.fval = lay.fval_smem ? reinterpret_cast<double*>(wb + lay.o_fval) : ws_fval + rr * (size_t)(m + 1);
+    if (lay.sc_cap > 0) {
+        w.scp = reinterpret_cast<double*>(wb + lay.o_scp);
+        w.scq = reinterpret_cast<double*>(wb + lay.o_scq);
+        w.scr = reinterpret_cast<double*>(wb + lay.o_scr);
+        w.screl = reinterpret_cast<int*>(wb + lay.o_screl);
+    } else {
+        w.scp = ws_scr + rr * 3 * (size_t)P.max_inc;
+        w.scq = w.scp + P.max_inc;
+        w.scr = w.scq + P.max_inc;
+        w.screl = ws_screl + rr * (size_t)P.max_inc;
+    }
+
+    MtRng rng;
+    rng.key = w.mt;
+    rng.pos = 624;
+    int phase = PH_DONE;
+    qcqp_cd_stats st;
+    st.steps_p1 = st.steps_p2 = st.updates_p1 = st.updates_p2 = 0;
+    st.sweeps_p1 = st.sweeps_p2 = 0; st.status = QCQP_RUN_OK; st.ran_phase2 = 0;
+
+    if (live) {
+        for (int i = lane; i < n; i += 32) w.x[i] = X0[rr * n + i];
+        for (int i = lane; i < 624; i += 32) w.mt[i] = rngs[rr].key[i];
+        rng.pos = rngs[rr].pos;
+        phase = PH_P1;
+    }
+    __syncwarp();
+
+    const bool strict = prm.strict != 0;
+    const double tol = prm.tol, viol_tol = prm.viol_tol;
+    int t = 0;                    // sweeps done in the current phase
+    long long update_counter = 0;
+    double viol_last = QCQP_INF;  // phase 1
+    double viol_p2 = 0.0;         // phase 2: frozen at entry (qcqp.py:157)
+    bool p1_over = live && !prm.phase1;
+    unsigned slot = 0;
+
+    for (;;) {
+        // ---------------- sweep boundary: phase transitions (warp-uniform) ----------------
+        if (phase == PH_P1) {
+            if (p1_over || t >= prm.num_iters || viol_last < viol_tol) {
+                // improve_coord_descent: if max(prob.violations(x)) < viol_tol: phase 2   (qcqp.py:189-190)
+                double mv = refresh_fvals(P, w, 0, strict, lane);
+                if (m == 0) { st.status = QCQP_RUN_EMPTY_MAX; phase = PH_DONE; }
+                else if (mv < viol_tol) { phase = PH_P2; viol_p2 = mv; t = 0; update_counter = 0; st.ran_phase2 = 1; }
+                else phase = PH_DONE;
+            } else if (t == 0) {
+                refresh_fvals(P, w, 1, strict, lane);
+            }
+        }
+        if (phase == PH_P2 && t >= prm.num_iters) phase = PH_DONE;
+        if (ring) {
+            if (!__syncthreads_or(phase != PH_DONE)) break;
+        } else if (phase == PH_DONE) break;
+        if (phase == PH_P1) st.sweeps_p1++;
+        if (phase == PH_P2) st.sweeps_p2++;
+        bool skip = false;   // phase 1 'failed' break: the rest of this sweep is not executed (qcqp.py:138-141)
+
+        int nx_beg = P.inc_ptr[0], nx_end = P.inc_ptr[1];
+        for (int k = 0; k < n; k++, slot++) {
+            const int beg = nx_beg, end = nx_end;
+            if (k + 1 < n) { nx_beg = end; nx_end = P.inc_ptr[k + 2]; }
+            const bool work = (phase != PH_DONE) && !skip;
+            // ---- dense rows of this coordinate: dot each against z ----
+            if (ring) {
+                const int sg = slot % S;
+                mbar_wait(&bar_full[sg], (slot / S) & 1);
+                if (work) {
+                    const double* rows = ringbuf + (size_t)sg * nd * ld;
+                    if (!strict) {
+                        for (int d = (phase == PH_P1 && P.dense_form[0] == 0) ? 1 : 0; d < nd; d++) {
+                            double v = dense_row_dot_warp(rows + (size_t)d * ld, w.x, n, k, lane);
+                            if (lane == 0) w.dd[d] = v;
+                        }
+                    } else {
+                        for (int d = lane; d < nd; d += 32) w.dd[d] = dense_row_dot_seq(rows + (size_t)d * ld, w.x, n, k);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[sg]);
+            }
+            if (!work) {
+                if (!ring) break;
+                continue;
+            }
+            const double xk = w.x[k];
+            // ---- one-variable coefficients of the incident forms (get_onevar_func, utilities.py:99-105) ----
+            const bool has_obj = (end > beg) && ((P.inc_form[beg] & INC_FORM_MASK) == 0);
+            const int cbeg = beg + (has_obj ? 1 : 0);
+            const int mk = end - cbeg;
+            double p0 = 0.0, q0 = 0.0, r0 = 0.0;
+            if (phase == PH_P2) {
+                r0 = w.fval[0];
+                if (has_obj) {
+                    uint32_t fw = P.inc_form[beg];
+                    double dot;
+                    if (fw & INC_DENSE_BIT) dot = w.dd[P.dense_slot[0]];
+                    else if (strict) dot = sparse_row_dot_seq(P, beg, w.x);
+                    else dot = sparse_row_dot_warp(P, beg, w.x, lane);
+                    p0 = P.inc_t2[beg];
+                    q0 = 2 * dot + P.inc_qk[beg];
+                    r0 = w.fval[0] - xk * (p0 * xk + q0);
+                }
+            }
+            for (int base = 0; base < mk; base += 32) {
+                const int i = base + lane;
+                const bool mine = i < mk;
+                const int e = cbeg + (mine ? i : 0);
+                uint32_t fw = 0;
+                double dot = 0.0;
+                bool deferred = false;
+                if (mine) {
+                    fw = P.inc_form[e];
+                    if (fw & INC_DENSE_BIT) dot = w.dd[P.dense_slot[fw & INC_FORM_MASK]];
+                    else if (strict || P.row_ptr[e + 1] - P.row_ptr[e] <= CD_LONG_ROW) dot = sparse_row_dot_seq(P, e, w.x);
+                    else deferred = true;
+                }
+                unsigned coop = __ballot_sync(FULL, deferred);
+                while (coop) {
+                    int src = __ffs(coop) - 1;
+                    coop &= coop - 1;
+                    double v = sparse_row_dot_warp(P, cbeg + base + src, w.x, lane);
+                    if (lane == src) dot = v;
+                }
+                if (mine) {
+                    const int j = fw & INC_FORM_MASK;
+                    const double t2 = P.inc_t2[e];
+                    const double t1 = 2 * dot + P.inc_qk[e];
+                    w.scp[i] = t2;
+                    w.scq[i] = t1;
+                    w.scr[i] = w.fval[j] - xk * (t2 * xk + t1);
+                    w.screl[i] = (fw >> INC_RELOP_SHIFT) & 3;
+                }
+            }
+            __syncwarp();
+
+            double new_xi = xk;
+            bool move = false;
+            if (phase == PH_P1) {
+                // ---- phase 1: bisect the violation level (qcqp.py:113-141) ----
+                st.steps_p1++;
+                double vmax = -QCQP_INF;
+                int cnt = 0;
+                for (int i = lane; i < mk; i += 32) {
+                    double p = w.scp[i], q = w.scq[i];
+                    if (p == 0.0 && q == 0.0) continue;
+                    cnt++;
+                    double v = violation_of(w.screl[i], onevar_eval(p, q, w.scr[i], xk));
+                    vmax = (v > vmax) ? v : vmax;
+                }
+                cnt = warp_sum_i(cnt);
+                if (cnt == 0) { st.status = QCQP_RUN_EMPTY_MAX; phase = PH_DONE; continue; }
+                const double viol = warp_max(vmax);
+                double new_viol = viol;
+                double ss = -tol, es = viol - viol_tol;
+                while (es - ss > tol) {
+                    double s = (ss + es) / 2;
+                    double xi;
+                    int err;
+                    int ok = solve_level(w, mk, s, 0.0, 0.0, 0.0, rng, lay.evN, lane, &xi, &err);
+                    if (err) { st.status = err; break; }
+                    if (!ok) ss = s;
+                    else { new_xi = xi; new_viol = s; es = s; }
+                }
+                if (st.status != QCQP_RUN_OK) { phase = PH_DONE; continue; }
+                if (new_viol < viol) { move = true; update_counter = 0; st.updates_p1++; }
+                else {
+                    update_counter++;
+                    if (update_counter == n) skip = true;
+                }
+            } else {
+                // ---- phase 2: minimise the objective at the frozen level (qcqp.py:162-176) ----
+                st.steps_p2++;
+                double xi;
+                int err;
+                int ok = solve_level(w, mk, viol_p2, p0, q0, r0, rng, lay.evN, lane, &xi, &err);
+                if (err) { st.status = err; phase = PH_DONE; continue; }
+                if (ok && fabs(xi - xk) > tol) { move = true; new_xi = xi; update_counter = 0; st.updates_p2++; }
+                else {
+                    update_counter++;
+                    if (update_counter == n) phase = PH_DONE;   // converged
+                }
+            }
+            if (move) {
+                // f_j(x) = t0 + b (t2 b + t1) for every incident form
+                const double b = new_xi;
+                for (int i = lane; i < mk; i += 32) {
+                    int j = P.inc_form[cbeg + i] & INC_FORM_MASK;
+                    w.fval[j] = w.scr[i] + b * (w.scp[i] * b + w.scq[i]);
+                }
+                if (lane == 0) {
+                    if (phase != PH_P1 && has_obj) w.fval[0] = r0 + b * (p0 * b + q0);
+                    w.x[k] = b;
+                }
+                __syncwarp();
+            }
+        }
+        // ---------------- end of sweep ----------------
+        if (phase == PH_P1) {
+            double mv = refresh_fvals(P, w, 1, strict, lane);   // viol = max(prob.violations(x))  (qcqp.py:142)
+            viol_last = mv;
+            t++;
+        } else if (phase == PH_P2) {
+            t++;
+            if (prm.refresh_every > 0 && (t % prm.refresh_every) == 0) refresh_fvals(P, w, 0, strict, lane);
+        }
+    }
+
+    // ---------------- results: x, (f0.eval(x), max(violations(x))) as QCQP._improve returns them (qcqp.py:415-417) -------
+    if (live) {
+        double mv = refresh_fvals(P, w, 0, strict, lane);
+        for (int i = lane; i < n; i += 32) X[rr * n + i] = w.x[i];
+        for (int i = lane; i < 624; i += 32) rngs[rr].key[i] = w.mt[i];
+        if (lane == 0) {
+            rngs[rr].pos = rng.pos;
+            f0_out[rr] = w.fval[0];
+            mv_out[rr] = (m > 0) ? mv : 0.0;
+            if (stats_out) stats_out[rr] = st;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: shared-memory plan and launch
+// ---------------------------------------------------------------------------------------------------------
+static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
+
+static int plan_layout(const qcqp_pack* p, int R, CdLayout* L)
+{
+    const PackView& v = p->v;
+    const int smem_max = max_smem_optin(p->device);
+    const int sms = num_sms(p->device);
+    CdLayout l;
+    memset(&l, 0, sizeof(l));
+    int evN = 8;
+    while (evN < v.ev_cap) evN <<= 1;
+    l.evN = evN;
+    l.sc_cap = (v.max_inc <= 1024) ? (v.max_inc > 0 ? v.max_inc : 1) : 0;
+    l.fval_smem = ((size_t)(v.m + 1) * 8 <= 24 * 1024) ? 1 : 0;
+    unsigned o = 0;
+    l.o_x = o; o += align_up((unsigned)v.n * 8, 16);
+    l.o_fval = o; if (l.fval_smem) o += align_up((unsigned)(v.m + 1) * 8, 16);
+    l.o_mt = o; o += 624 * 4;
+    l.o_scp = o; o += align_up((unsigned)l.sc_cap * 8, 16);
+    l.o_scq = o; o += align_up((unsigned)l.sc_cap * 8, 16);
+    l.o_scr = o; o += align_up((unsigned)l.sc_cap * 8, 16);
+    l.o_screl = o; o += align_up((unsigned)l.sc_cap * 4, 16);
+    l.o_evk = o; o += (unsigned)evN * 8;
+    l.o_evd = o; o += (unsigned)evN * 4;
+    l.o_clo = o; o += align_up((unsigned)(evN / 2 + 2) * 8, 16);
+    l.o_chi = o; o += align_up((unsigned)(evN / 2 + 2) * 8, 16);
+    l.o_dd = o; o += align_up((unsigned)(v.n_dense > 0 ? v.n_dense : 1) * 8, 16);
+    l.o_misc = o; o += 16;
+    l.warp_stride = align_up(o, 128);
+
+    const unsigned stage_bytes = (unsigned)v.n_dense * v.ld * 8;
+    int W, S = 0;
+    if (v.n_dense > 0) {
+        S = 4;
+        while (S > 2 && (size_t)S * stage_bytes > (size_t)smem_max / 3) S--;
+        unsigned fixed = 256 + align_up(S * stage_bytes, 128);
+        if (fixed + l.warp_stride > (unsigned)smem_max)
+            return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: one restart plus the dense-row ring exceeds shared memory");
+        int wmax = (int)((smem_max - fixed) / l.warp_stride);
+        if (wmax > 15) wmax = 15;
+        W = (R + sms - 1) / sms;          // spread the restarts over all SMs first, then share rows inside a CTA
+        if (W < 1) W = 1;
+        if (W > wmax) W = wmax;
+        l.off_bar = 0;
+        l.off_ring = 256;
+        l.off_warp0 = fixed;
+    } else {
+        if (l.warp_stride > (unsigned)smem_max)
+            return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: per-restart state exceeds shared memory (too many two-interval constraints on one coordinate)");
+        int wmax = (int)(smem_max / l.warp_stride);
+        W = wmax < 4 ? wmax : 4;
+        if (W < 1) W = 1;
+        l.off_bar = 0; l.off_ring = 0; l.off_warp0 = 0;
+    }
+    l.W = W; l.S = S;
+    l.total = l.off_warp0 + (unsigned)W * l.warp_stride;
+    *L = l;
+    return QCQP_OK;
+}
+
+int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0,
+              double* dmv, qcqp_cd_stats* dstats, cudaStream_t stream)
+{
+    if (R <= 0) return QCQP_OK;
+    CdLayout L;
+    int rc = plan_layout(p, R, &L);
+    if (rc != QCQP_OK) return rc;
+    const PackView& v = p->v;
+    size_t fval_bytes = L.fval_smem ? 0 : (size_t)R * (v.m + 1) * 8;
+    size_t scr_bytes = L.sc_cap > 0 ? 0 : (size_t)R * 3 * v.max_inc * 8;
+    size_t rel_bytes = L.sc_cap > 0 ? 0 : (size_t)R * v.max_inc * 4;
+    size_t a1 = (fval_bytes + 255) & ~(size_t)255, a2 = (scr_bytes + 255) & ~(size_t)255;
+    rc = ensure_workspace(p, a1 + a2 + rel_bytes + 256);
+    if (rc != QCQP_OK) return rc;
+    double* ws_fval = (double*)p->ws;
+    double* ws_scr = (double*)((char*)p->ws + a1);
+    int* ws_rel = (int*)((char*)p->ws + a1 + a2);
+    CdK k;
+    k.num_iters = prm->num_iters; k.viol_tol = prm->viol_tol; k.tol = prm->tol;
+    k.phase1 = prm->phase1; k.strict = prm->strict;
+    k.refresh_every = prm->refresh_every > 0 ? prm->refresh_every : 64;
+    QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    int blocks = (R + L.W - 1) / L.W;
+    int threads = (L.W + (v.n_dense > 0 ? 1 : 0)) * 32;
+    cd_kernel<<<blocks, threads, L.total, stream>>>(v, k, L, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_rel);
+    QCQP_CUDA_TRY(cudaGetLastError());
+    return QCQP_OK;
+}
+
+}  // namespace qcqp

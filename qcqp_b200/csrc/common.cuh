@@ -1,0 +1,170 @@
+// common.cuh -- shared declarations of libqcqp_b200: error plumbing, the device-side pack view, warp helpers,
+// mbarrier / bulk-copy (TMA) PTX wrappers for sm_100a.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qcqp_b200.h"
+
+namespace qcqp {
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define QCQP_CUDA_TRY(expr)                                                                                 \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess)                                                                           \
+            return ::qcqp::fail(QCQP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// device view of a pack (plain pointers; passed to kernels by value)
+//
+// HBM layout (DESIGN.md "data layout"):
+//   coordinate-major incidence, for the CD sweep:
+//     inc_ptr[n+1]; for incidence e in [inc_ptr[k], inc_ptr[k+1]):  (forms in ascending j; objective first)
+//       inc_form[e]  = j | relop_j << 28 | dense << 31     inc_t2[e] = P_j[k,k]     inc_qk[e] = q_j[k]
+//       off-diagonal entries of row k of P_j: row_col/row_val[row_ptr[e] .. row_ptr[e+1])  (sorted by column;
+//       empty for forms stored dense)
+//   form-major COO, for f_j(x) from scratch:
+//     f_ptr[m+2]; entries (f_row, f_col, f_val) sorted by (row, col);  q_ptr[m+2]; (q_idx, q_val); r[m+1]; relop[m+1]
+//   dense forms: dense_P[slot][n][ld] row-major, ld = n rounded up to even (16-byte rows for cp.async.bulk)
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t INC_FORM_MASK = 0x0fffffffu;
+constexpr int INC_RELOP_SHIFT = 28;
+constexpr uint32_t INC_DENSE_BIT = 0x80000000u;
+
+struct PackView {
+    int n, m, n_dense, ld;
+    int max_inc;     // max incidences of one coordinate
+    int ev_cap;      // event slots the 1-D sweep-line can need (4 per two-interval-capable incidence + 4)
+    const int* inc_ptr;
+    const uint32_t* inc_form;
+    const double* inc_t2;
+    const double* inc_qk;
+    const int* row_ptr;
+    const int* row_col;
+    const double* row_val;
+    const long long* f_ptr;
+    const int* f_row;
+    const int* f_col;
+    const double* f_val;
+    const long long* q_ptr;
+    const int* q_idx;
+    const double* q_val;
+    const double* r;
+    const int* relop;
+    const int* dense_slot;   // [m+1]: slot or -1
+    const int* dense_form;   // [n_dense]: form of slot
+    const double* dense_P;   // [n_dense][n][ld]
+    // ADMM (set by qcqp_admm_pack_eig)
+    const double* eig_lambda;  // [m][n]
+    const double* eig_Q;       // [m][n][n]   Q_i[a][b]: component a of eigenvector b
+    const double* eig_Qt;      // [m][n][n]   transposed copy, so both Q^T v and Q xhat read rows coalesced
+    const double* eig_qhat;    // [m][n]
+};
+
+}  // namespace qcqp
+
+// the opaque handle of the C ABI
+struct qcqp_pack {
+    qcqp::PackView v;
+    qcqp_pack_info info;
+    int device;
+    std::vector<void*> allocs;   // every cudaMalloc owned by the pack
+    // workspace, grown on demand
+    void* ws;
+    size_t ws_bytes;
+    bool has_eig;
+    int objective_dense;
+};
+
+namespace qcqp {
+
+int ensure_workspace(qcqp_pack* p, size_t bytes);
+int num_sms(int device);
+int max_smem_optin(int device);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { double w = __shfl_xor_sync(FULL, v, o); v = (w > v) ? w : v; }
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ int bcast_i(int v, int src) { return __shfl_sync(FULL, v, src); }
+
+// ---------------------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA unit, non-tensor form) -- SASS: SYNCS.* / UBLKCP
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy; bytes and both addresses must be multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace qcqp

@@ -1,0 +1,101 @@
+// forms_eval.cuh -- f_j(x) = x'P_j x + q_j'x + r_j from scratch, for one point held by one warp
+// (QuadraticFunction.eval, utilities.py:49-50).  Used by the CD kernel (cache refresh, final (f0, maxviol)),
+// the batched eval kernel and the SDR sampler.
+#pragma once
+
+#include "common.cuh"
+
+namespace qcqp {
+
+constexpr int EVAL_LONG_FORM = 96;   // sparse forms with more stored entries than this are summed by the whole warp
+
+// One lane, one sparse form, in the reference's order: rows ascending, (P x)_i summed over ascending columns with
+// separately rounded multiply/add (SciPy csr_matvec), then acc += ((P x)_i + q_i) * x_i, then + r.
+__device__ __forceinline__ double eval_sparse_form_seq(const PackView& P, int j, const double* x)
+{
+    long long e = P.f_ptr[j], pe = P.f_ptr[j + 1];
+    long long qe = P.q_ptr[j], qend = P.q_ptr[j + 1];
+    double acc = 0.0;
+    while (e < pe || qe < qend) {
+        int ip = (e < pe) ? P.f_row[e] : 0x7fffffff;
+        int iq = (qe < qend) ? P.q_idx[qe] : 0x7fffffff;
+        int i = ip < iq ? ip : iq;
+        double y = 0.0;
+        while (e < pe && P.f_row[e] == i) { y = y + P.f_val[e] * x[P.f_col[e]]; e++; }
+        if (iq == i) { y = y + P.q_val[qe]; qe++; }
+        acc = acc + y * x[i];
+    }
+    return acc + P.r[j];
+}
+
+// whole warp, one sparse form (fast mode): fma partial sums, one shuffle reduction
+__device__ __forceinline__ double eval_sparse_form_warp(const PackView& P, int j, const double* x, int lane)
+{
+    double acc = 0.0;
+    for (long long e = P.f_ptr[j] + lane; e < P.f_ptr[j + 1]; e += 32) acc = fma(P.f_val[e] * x[P.f_row[e]], x[P.f_col[e]], acc);
+    for (long long e = P.q_ptr[j] + lane; e < P.q_ptr[j + 1]; e += 32) acc = fma(P.q_val[e], x[P.q_idx[e]], acc);
+    return warp_sum(acc) + P.r[j];
+}
+
+// whole warp, one dense form (fast mode): lanes own columns, rows stream from HBM/L2 coalesced
+__device__ __forceinline__ double eval_dense_form_warp(const PackView& P, int j, const double* x, int lane)
+{
+    const int n = P.n, ld = P.ld;
+    const double* M = P.dense_P + (size_t)P.dense_slot[j] * n * ld;
+    double acc = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double* row = M + (size_t)i * ld;
+        double part = 0.0;
+        for (int c = lane; c < n; c += 32) part = fma(row[c], x[c], part);
+        acc = fma(part, x[i], acc);
+    }
+    for (long long e = P.q_ptr[j] + lane; e < P.q_ptr[j + 1]; e += 32) acc = fma(P.q_val[e], x[P.q_idx[e]], acc);
+    return warp_sum(acc) + P.r[j];
+}
+
+// one lane, one dense form, reference order (strict mode; slow, test sizes only)
+__device__ __forceinline__ double eval_dense_form_seq(const PackView& P, int j, const double* x)
+{
+    const int n = P.n, ld = P.ld;
+    const double* M = P.dense_P + (size_t)P.dense_slot[j] * n * ld;
+    long long qe = P.q_ptr[j], qend = P.q_ptr[j + 1];
+    double acc = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double* row = M + (size_t)i * ld;
+        double y = 0.0;
+        for (int c = 0; c < n; c++) {
+            double v = row[c];
+            if (v != 0.0) y = y + v * x[c];   // CSR stores no explicit zeros
+        }
+        if (qe < qend && P.q_idx[qe] == i) { y = y + P.q_val[qe]; qe++; }
+        acc = acc + y * x[i];
+    }
+    return acc + P.r[j];
+}
+
+// f_j(x) for j in [j0, j1], every result handed to sink(j, value) by exactly one lane.
+// Short sparse forms: one lane each.  Long sparse and dense forms: the whole warp (fast) or one lane (strict).
+template <class Sink>
+__device__ __forceinline__ void eval_forms(const PackView& P, const double* x, int j0, int j1, bool strict, int lane, Sink sink)
+{
+    for (int base = j0; base <= j1; base += 32) {
+        int j = base + lane;
+        bool mine = j <= j1;
+        bool dense = mine && P.dense_slot[j] >= 0;
+        bool big = mine && !dense && (P.f_ptr[j + 1] - P.f_ptr[j]) > EVAL_LONG_FORM;
+        if (mine && !dense && (!big || strict)) sink(j, eval_sparse_form_seq(P, j, x));
+        if (mine && dense && strict) sink(j, eval_dense_form_seq(P, j, x));
+        if (!strict) {
+            unsigned coop = __ballot_sync(FULL, dense || big);
+            while (coop) {
+                int src = __ffs(coop) - 1;
+                coop &= coop - 1;
+                int jj = base + src;
+                double v = (P.dense_slot[jj] >= 0) ? eval_dense_form_warp(P, jj, x, lane) : eval_sparse_form_warp(P, jj, x, lane);
+                if (lane == src) sink(jj, v);
+            }
+        }
+    }
+}
+
+}  // namespace qcqp

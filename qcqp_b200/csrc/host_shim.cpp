@@ -1,0 +1,68 @@
+// host_shim.cpp -- TEST-ONLY: exposes the __host__ __device__ 1-D solver of onevar.cuh to the CPU test-suite
+// (tests/test_onevar_host.py), so the device logic (intervals, fold, sweep line, minimiser choice, MT19937) can be
+// checked against the golden vectors on the GPU-less build box.  Built as libqcqp_b200_hostshim.so; it is NOT part of
+// libqcqp_b200.so and the qcqp_b200 package never loads it.
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/qcqp_b200.h"
+#include "onevar.cuh"
+
+using namespace qcqp;
+
+// single-thread composition of the pieces the CD kernel runs per warp (cd.cu: solve_level)
+extern "C" int qcqp_shim_onevar_qcqp(const double* f0 /*p,q,r*/, const double* fs /*[m][3]*/, const int32_t* relops, int32_t m,
+                                     double s, qcqp_rng_state* st, double* xout)
+{
+    std::vector<double> ev_key(4 * (size_t)m + 8), c_lo(2 * (size_t)m + 4), c_hi(2 * (size_t)m + 4);
+    std::vector<int> ev_del(4 * (size_t)m + 8);
+    Fold fold;
+    fold.init();
+    int nev = 0;
+    for (int i = 0; i < m; i++) {
+        double p = fs[3 * i], q = fs[3 * i + 1], r = fs[3 * i + 2];
+        fold.mcnt++;   // the caller has already dropped (p, q) == (0, 0) forms, as qcqp.py:116 does
+        Ival I[2];
+        int c = feasible_intervals(p, q, r, relops[i], s, I);
+        if (c == 0) fold.nempty++;
+        else if (c == 1) fold.add_single(I[0].lo, I[0].hi);
+        else {
+            ev_key[nev] = I[0].lo; ev_del[nev++] = +1; ev_key[nev] = I[0].hi; ev_del[nev++] = -1;
+            ev_key[nev] = I[1].lo; ev_del[nev++] = +1; ev_key[nev] = I[1].hi; ev_del[nev++] = -1;
+        }
+    }
+    if (fold.nempty > 0) return 0;
+    nev = finish_events(fold, ev_key.data(), ev_del.data(), nev);
+    insertion_sort_events(ev_key.data(), ev_del.data(), nev);
+    int nC = sweep_sorted(ev_key.data(), ev_del.data(), nev, fold.mcnt, c_lo.data(), c_hi.data());
+    MtRng rng{st->key, st->pos};
+    int err = 0;
+    int ok = choose_point(f0[0], f0[1], f0[2], c_lo.data(), c_hi.data(), nC, rng, xout, &err);
+    st->pos = rng.pos;
+    return err ? -err : ok;
+}
+
+extern "C" int qcqp_shim_feasible_intervals(double p, double q, double r, int32_t relop, double s, double* out4)
+{
+    Ival I[2];
+    int c = feasible_intervals(p, q, r, relop, s, I);
+    for (int i = 0; i < c; i++) { out4[2 * i] = I[i].lo; out4[2 * i + 1] = I[i].hi; }
+    return c;
+}
+
+extern "C" double qcqp_shim_uniform(qcqp_rng_state* st, double lo, double hi)
+{
+    MtRng rng{st->key, st->pos};
+    double v = rng.uniform(lo, hi);
+    st->pos = rng.pos;
+    return v;
+}
+
+extern "C" int qcqp_shim_choice(qcqp_rng_state* st, int32_t n)
+{
+    MtRng rng{st->key, st->pos};
+    int v = rng.choice(n);
+    st->pos = rng.pos;
+    return v;
+}

@@ -1,0 +1,291 @@
+// onevar.cuh -- the 1-D machinery of the coordinate-descent sweep, written for one lane of a warp:
+//   * MT19937 + NumPy's legacy uniform/choice transforms (the reference consumes np.random, SURVEY a-7)
+//   * feasible set of one scalar quadratic constraint            (get_feasible_intervals, utilities.py:198-232)
+//   * the sweep-line intersection with the reference's quirks     (onevar_qcqp, utilities.py:241-261)
+//   * the choice of the minimiser over the feasible set           (onevar_qcqp, utilities.py:263-288)
+//
+// GPU formulation (not the reference's): constraints whose feasible set is ONE interval are folded into a running
+// (L = max lo, H = min hi, multiplicity of H, count); only two-interval constraints contribute explicit events.
+// The fold is exact with respect to the reference's dict/sorted sweep, including its quirks -- a feasible piece is
+// reported only where the running total drops to m by exactly -1, so two coincident right ends hide it, a piece
+// unbounded to the right is never seen, zero-width pieces cancel (DESIGN.md "1-D solver" has the argument).
+//
+// Everything here is __host__ __device__ so that tests/ can run the same code on the CPU build box through
+// csrc/host_shim.cpp (unit tests of device code; the product never runs it on the host).
+// Compile with -fmad=false: NumPy rounds every multiply and add separately and the branch thresholds depend on it.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QCQP_HD __host__ __device__ __forceinline__
+#else
+#define QCQP_HD inline
+#endif
+
+namespace qcqp {
+
+#ifndef QCQP_INF
+#define QCQP_INF (__builtin_huge_val())
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// MT19937, sequential (one lane owns the stream)
+// ---------------------------------------------------------------------------------------------------------
+struct MtRng {
+    uint32_t* key;  // [624]
+    int pos;
+
+    QCQP_HD void refill()
+    {
+        uint32_t* mt = key;
+        int i;
+        for (i = 0; i < 624 - 397; i++) {
+            uint32_t y = (mt[i] & 0x80000000u) | (mt[i + 1] & 0x7fffffffu);
+            mt[i] = mt[i + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        for (; i < 623; i++) {
+            uint32_t y = (mt[i] & 0x80000000u) | (mt[i + 1] & 0x7fffffffu);
+            mt[i] = mt[i - 227] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        pos = 0;
+    }
+    QCQP_HD uint32_t next()
+    {
+        if (pos >= 624) refill();
+        uint32_t y = key[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    // random_sample(): 53-bit double from two draws
+    QCQP_HD double next_double()
+    {
+        uint32_t a = next() >> 5, b = next() >> 6;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+    // np.random.uniform(lo, hi)
+    QCQP_HD double uniform(double lo, double hi)
+    {
+        double range = hi - lo;
+        return lo + range * next_double();
+    }
+    // np.random.choice(cnt) == legacy randint(0, cnt): masked rejection; cnt == 1 draws nothing
+    QCQP_HD int choice(int cnt)
+    {
+        uint32_t top = (uint32_t)(cnt - 1);
+        if (top == 0) return 0;
+        uint32_t mask = top;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        do { v = next() & mask; } while (v > top);
+        return (int)v;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// scalar quadratic p x^2 + q x + r
+// ---------------------------------------------------------------------------------------------------------
+QCQP_HD bool is_inf(double x) { return x == QCQP_INF || x == -QCQP_INF; }
+
+// OneVarQuadraticFunction.eval (utilities.py:115-120)
+QCQP_HD double onevar_eval(double p, double q, double r, double x)
+{
+    if (is_inf(x)) {
+        if (p != 0.0) return p * x * x;
+        if (q != 0.0) return q * x;
+        return r;
+    }
+    return x * (p * x + q) + r;
+}
+
+// QuadraticFunction.violation (utilities.py:56-62)
+QCQP_HD double violation_of(int relop, double v)
+{
+    if (relop == QCQP_RELOP_EQ) return fabs(v);
+    return (v > 0.0) ? v : 0.0;
+}
+
+struct Ival { double lo, hi; };
+
+constexpr double IVAL_TOL = 1e-4;  // the default tol of get_feasible_intervals; the reference never overrides it
+
+// {x : p x^2 + q x + rr <= 0}; the '<=' branch of utilities.py:210-231 with s already folded into rr
+QCQP_HD int ivals_le0(double p, double q, double rr, Ival* out)
+{
+    if (p > IVAL_TOL) {
+        double D = q * q - (4 * p) * rr;
+        if (D >= 0) {
+            double rD = sqrt(D), den = 2 * p;
+            out[0].lo = (-q - rD) / den;
+            out[0].hi = (-q + rD) / den;
+            return 1;
+        }
+        return 0;
+    }
+    if (p < -IVAL_TOL) {
+        double D = q * q - (4 * p) * rr;
+        if (D >= 0) {
+            double rD = sqrt(D), den = 2 * p;
+            out[0].lo = -QCQP_INF; out[0].hi = (-q + rD) / den;
+            out[1].lo = (-q - rD) / den; out[1].hi = QCQP_INF;
+            return 2;
+        }
+        out[0].lo = -QCQP_INF; out[0].hi = QCQP_INF;
+        return 1;
+    }
+    if (q > IVAL_TOL) { out[0].lo = -QCQP_INF; out[0].hi = (0.0 - rr) / q; return 1; }
+    if (q < -IVAL_TOL) { out[0].lo = (0.0 - rr) / q; out[0].hi = QCQP_INF; return 1; }
+    out[0].lo = -QCQP_INF; out[0].hi = QCQP_INF;
+    return 1;
+}
+
+// get_feasible_intervals(f, s) (utilities.py:198-232); at most two intervals come out
+QCQP_HD int feasible_intervals(double p, double q, double r, int relop, double s, Ival* out)
+{
+    if (relop != QCQP_RELOP_EQ) {
+        // (r - s) folded: the reference computes q*q - 4*p*(r-s) and (s-r)/q.  (s-r) == -(r-s) exactly in IEEE, and
+        // 0.0 - (r-s) reproduces it including the sign of zero.
+        return ivals_le0(p, q, r - s, out);
+    }
+    Ival a[2], b[2];
+    int na = ivals_le0(p, q, r - s, a);       // f1 = (p, q, r - s) <= 0
+    int nb = ivals_le0(-p, -q, -r - s, b);    // f2 = (-p, -q, -r - s) <= 0
+    int c = 0;
+    for (int i = 0; i < na; i++)
+        for (int k = 0; k < nb; k++) {
+            double lo = (b[k].lo > a[i].lo) ? b[k].lo : a[i].lo;
+            double hi = (b[k].hi < a[i].hi) ? b[k].hi : a[i].hi;
+            if (lo <= hi) {
+                if (c < 2) { out[c].lo = lo; out[c].hi = hi; }
+                c++;
+            }
+        }
+    return c > 2 ? 2 : c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// running fold of the single-interval constraints
+// ---------------------------------------------------------------------------------------------------------
+struct Fold {
+    double L, H;    // max of the left ends, min of the right ends
+    int mu;         // how many right ends equal H exactly
+    int m1;         // single-interval constraints folded
+    int mcnt;       // constraints counted (those with (p, q) != (0, 0): qcqp.py:116,166)
+    int nempty;     // constraints with an empty feasible set
+
+    QCQP_HD void init() { L = -QCQP_INF; H = QCQP_INF; mu = 0; m1 = 0; mcnt = 0; nempty = 0; }
+    QCQP_HD void add_single(double lo, double hi)
+    {
+        m1++;
+        if (lo > L) L = lo;
+        if (hi < H) { H = hi; mu = 1; }
+        else if (hi == H) mu++;
+    }
+    QCQP_HD void merge(double L2, double H2, int mu2, int m12, int mcnt2, int nempty2)
+    {
+        if (L2 > L) L = L2;
+        if (m12 > 0) {
+            if (m1 == 0 || H2 < H) { H = H2; mu = mu2; }
+            else if (H2 == H) mu += mu2;
+        }
+        m1 += m12; mcnt += mcnt2; nempty += nempty2;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// sweep line over the explicit events (utilities.py:245-261).
+// ev_key/ev_del hold nev events already SORTED by key (ties in any order).  mcnt = len(fs).
+// Feasible pieces are appended to (c_lo, c_hi); returns their number.
+// ---------------------------------------------------------------------------------------------------------
+QCQP_HD int sweep_sorted(const double* ev_key, const int* ev_del, int nev, int mcnt, double* c_lo, double* c_hi)
+{
+    int nC = 0;
+    long tot = 0;
+    double prev_key = 0.0;   // key of the previous entry with a nonzero net count
+    bool have_prev = false;
+    int i = 0;
+    while (i < nev) {
+        double key = ev_key[i];
+        int d = 0;
+        while (i < nev && ev_key[i] == key) { d += ev_del[i]; i++; }   // dict: equal keys share one counter
+        if (d == 0) continue;                                          // zero-net entries are dropped
+        tot += d;
+        if (tot == mcnt && d == -1 && have_prev) { c_lo[nC] = prev_key; c_hi[nC] = key; nC++; }
+        prev_key = key;
+        have_prev = true;
+    }
+    return nC;
+}
+
+QCQP_HD void insertion_sort_events(double* key, int* del, int nev)
+{
+    for (int i = 1; i < nev; i++) {
+        double k = key[i];
+        int d = del[i];
+        int j = i - 1;
+        while (j >= 0 && key[j] > k) { key[j + 1] = key[j]; del[j + 1] = del[j]; j--; }
+        key[j + 1] = k;
+        del[j + 1] = d;
+    }
+}
+
+// appends the sentinels and the folded single-interval constraints to the explicit (two-interval) events
+QCQP_HD int finish_events(const Fold& f, double* ev_key, int* ev_del, int nev)
+{
+    ev_key[nev] = -QCQP_INF; ev_del[nev] = +1; nev++;
+    ev_key[nev] = QCQP_INF; ev_del[nev] = -1; nev++;
+    if (f.m1 > 0) {
+        ev_key[nev] = f.L; ev_del[nev] = f.m1; nev++;
+        ev_key[nev] = f.H; ev_del[nev] = -f.mu; nev++;
+    }
+    return nev;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the minimiser of f0 = (p, q, r) over the pieces (utilities.py:263-288).  Returns 1 and *xout, 0 for None.
+// *err: QCQP_RUN_UNBOUNDED_UNIFORM when the reference would raise OverflowError.
+// ---------------------------------------------------------------------------------------------------------
+QCQP_HD int choose_point(double p, double q, double r, const double* c_lo, const double* c_hi, int nC, MtRng& rng,
+                         double* xout, int* err)
+{
+    if (nC == 0) return 0;
+    if (p == 0.0 && q == 0.0) {
+        int idx = rng.choice(nC);
+        double lo = c_lo[idx], hi = c_hi[idx];
+        if (is_inf(lo) || is_inf(hi)) { *err = QCQP_RUN_UNBOUNDED_UNIFORM; return 0; }
+        *xout = rng.uniform(lo, hi);
+        return 1;
+    }
+    const bool have_x0 = (p > 0.0);
+    const double x0 = have_x0 ? (-q / (2. * p)) : 0.0;
+    // pass 1: the unconstrained minimiser wins as soon as a piece contains it; otherwise the smallest endpoint value
+    double bestf = QCQP_INF;
+    for (int i = 0; i < nC; i++) {
+        double lo = c_lo[i], hi = c_hi[i];
+        if (have_x0 && lo <= x0 && x0 <= hi) { *xout = x0; return 1; }
+        double fl = onevar_eval(p, q, r, lo), fr = onevar_eval(p, q, r, hi);
+        if (fl < bestf) bestf = fl;
+        if (fr < bestf) bestf = fr;
+    }
+    // pass 2: endpoints attaining it, in order (the reference's bestxs list); NaN values never match
+    int cnt = 0;
+    for (int i = 0; i < nC; i++) {
+        if (onevar_eval(p, q, r, c_lo[i]) == bestf) cnt++;
+        if (onevar_eval(p, q, r, c_hi[i]) == bestf) cnt++;
+    }
+    if (cnt == 0) return 0;
+    int pick = rng.choice(cnt);
+    for (int i = 0; i < nC; i++) {
+        if (onevar_eval(p, q, r, c_lo[i]) == bestf) { if (pick == 0) { *xout = c_lo[i]; return 1; } pick--; }
+        if (onevar_eval(p, q, r, c_hi[i]) == bestf) { if (pick == 0) { *xout = c_hi[i]; return 1; } pick--; }
+    }
+    return 0;
+}
+
+}  // namespace qcqp

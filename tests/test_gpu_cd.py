@@ -1,0 +1,113 @@
+"""GPU parity tests of the coordinate-descent engine against the oracle, through the C ABI (qcqp_cd_improve)."""
+import numpy as np
+import pytest
+
+from helpers import forms_of, rel_close, GEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_and_pack(forms):
+    from oracle import oracle as orc
+    from qcqp_b200 import engine
+    return orc.Problem(forms), engine.Pack(forms)
+
+
+def _run_both(forms, X0, seeds, strict, **kw):
+    from oracle import oracle as orc
+    from qcqp_b200 import engine
+    P, pack = _oracle_and_pack(forms)
+    R = X0.shape[0]
+    rng_g = engine.rng_states(seeds=seeds)
+    Xg, fg, vg, sg = pack.cd_improve(X0, rng_g, strict=strict, **kw)
+    out = []
+    for r in range(R):
+        st = orc.RngState.from_seed(int(seeds[r]))
+        xo, so = P.improve_cd(X0[r], st, fast=True, **kw)
+        out.append((xo, P.eval(0, xo), P.max_violation(xo), so, st))
+    pack.close()
+    return (Xg, fg, vg, sg, rng_g), out
+
+
+def test_golden_cd_cases_strict_bit_exact(golden):
+    """Strict mode against the reference's own goldens: (f0, maxviol) to 1e-9 and the same MT19937 position."""
+    from qcqp_b200 import engine
+    for c in golden["cd"]:
+        if c["only_phase"] is not None or c["name"] == "beam_cd":
+            continue
+        forms, _ = forms_of(c)
+        pack = engine.Pack(forms)
+        x0 = np.array(c["x0"])
+        rs = np.random.RandomState(c["seed"]); rs.standard_normal(len(x0))
+        rng = engine.rng_states(states=[rs.get_state()])
+        X, f0, mv, st = pack.cd_improve(x0[None, :], rng, strict=True, **c["kwargs"])
+        assert st[0].status == 0, c["name"]
+        assert rel_close(f0[0], c["f0"], rtol=1e-9, atol=1e-9), (c["name"], f0[0], c["f0"])
+        assert rel_close(mv[0], c["maxviol"], rtol=1e-6, atol=1e-9), (c["name"], mv[0], c["maxviol"])
+        assert rel_close(X[0], c["x"], rtol=1e-9, atol=1e-9), c["name"]
+        assert rng[0].pos == c["rng"]["pos"], (c["name"], rng[0].pos)
+        pack.close()
+
+
+@pytest.mark.parametrize("gen,gargs,R,kw", [
+    ("bls", dict(n=10, m=15, seed=1), 8, {}),
+    ("bls", dict(n=48, m=70, seed=3), 16, {}),
+    ("bls", dict(n=130, m=180, seed=2), 6, {}),
+    ("maxcut", dict(n=25, p=0.2, seed=1), 8, dict(num_iters=40)),
+    ("maxcut", dict(n=60, p=0.1, seed=1), 8, dict(num_iters=30)),
+    ("circle", dict(ncirc=3), 6, dict(num_iters=10)),
+    ("circle", dict(ncirc=6), 4, dict(num_iters=5)),
+    ("random", dict(n=6, m=4, seed=0), 6, dict(num_iters=20)),
+    ("random", dict(n=9, m=12, seed=5, density=0.6), 6, dict(num_iters=15)),
+])
+def test_cd_strict_matches_oracle(gen, gargs, R, kw):
+    """Same x0, same per-restart seed: strict mode reproduces the oracle's (cached-f) run: x to 1e-9, identical
+    stream positions and step counts."""
+    forms, _ = GEN[gen](**gargs)
+    n = forms[0][1].size
+    rs = np.random.RandomState(123)
+    X0 = rs.randn(R, n) if gen != "circle" else np.abs(rs.randn(R, n)) * 3 + 0.5
+    seeds = 1000 + np.arange(R)
+    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, seeds, True, **kw)
+    for r in range(R):
+        xo, fo, vo, so, st = out[r]
+        assert sg[r].status == so.status
+        assert (sg[r].steps_p1, sg[r].steps_p2) == (so.steps_p1, so.steps_p2), (r, sg[r].steps_p1, so.steps_p1, sg[r].steps_p2, so.steps_p2)
+        assert rng_g[r].pos == st.pos, r
+        assert rel_close(Xg[r], xo, rtol=1e-9, atol=1e-9), r
+        assert rel_close(fg[r], fo, rtol=1e-9, atol=1e-9)
+        assert rel_close(vg[r], vo, rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.parametrize("gen,gargs,R", [
+    ("bls", dict(n=64, m=96, seed=1), 32),
+    ("bls", dict(n=200, m=300, seed=1), 16),
+])
+def test_cd_fast_matches_oracle_1e6(gen, gargs, R):
+    """The production (fast) mode: warp-parallel fma row dots.  North-star bar: 1e-6 relative on (objective, max violation)."""
+    forms, _ = GEN[gen](**gargs)
+    n = forms[0][1].size
+    rs = np.random.RandomState(7)
+    X0 = rs.randn(R, n)
+    seeds = 500 + np.arange(R)
+    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, seeds, False)
+    bad = 0
+    for r in range(R):
+        xo, fo, vo, so, st = out[r]
+        ok = rel_close(fg[r], fo, rtol=1e-6, atol=1e-9) and rel_close(vg[r], vo, rtol=1e-6, atol=1e-9)
+        bad += (not ok)
+    assert bad == 0, "%d of %d restarts differ from the oracle beyond 1e-6" % (bad, R)
+
+
+def test_cd_error_statuses():
+    """A coordinate that no constraint touches makes the reference raise in phase 1 (qcqp.py:117): status EMPTY_MAX."""
+    import scipy.sparse as sp
+    from qcqp_b200 import engine
+    n = 4
+    forms = [(sp.identity(n, format="csr"), np.zeros(n), 0.0, None)]
+    P = sp.csr_matrix(([1.0], ([0], [0])), shape=(n, n))
+    forms.append((P, np.zeros(n), -1.0, "=="))
+    pack = engine.Pack(forms)
+    X, f0, mv, st = pack.cd_improve(np.full((1, n), 3.0), engine.rng_states(seeds=[1]))
+    assert st[0].status == 1
+    pack.close()

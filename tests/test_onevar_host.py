@@ -1,0 +1,117 @@
+"""Unit tests of the DEVICE 1-D solver (qcqp_b200/csrc/onevar.cuh) compiled for the host through the test-only shim
+csrc/host_shim.cpp: golden quirk cases from the reference, then random cases against the oracle.  CPU only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "qcqp_b200", "csrc", "host_shim.cpp")
+SO = os.path.join(ROOT, "qcqp_b200", "libqcqp_b200_hostshim.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    hdr = os.path.join(ROOT, "qcqp_b200", "csrc", "onevar.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", SRC, "-o", SO])
+    L = C.CDLL(SO)
+    L.qcqp_shim_onevar_qcqp.restype = C.c_int
+    L.qcqp_shim_onevar_qcqp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
+    L.qcqp_shim_feasible_intervals.restype = C.c_int
+    L.qcqp_shim_feasible_intervals.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_void_p]
+    L.qcqp_shim_uniform.restype = C.c_double
+    L.qcqp_shim_uniform.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.qcqp_shim_choice.restype = C.c_int
+    L.qcqp_shim_choice.argtypes = [C.c_void_p, C.c_int32]
+    return L
+
+
+def _solve(shim, f0, fs, s, st):
+    f0a = np.ascontiguousarray(f0, dtype=np.float64)
+    fa = np.ascontiguousarray([f[:3] for f in fs], dtype=np.float64).reshape(-1, 3)
+    ra = np.ascontiguousarray([orc.RELOP_CODE[f[3]] for f in fs], dtype=np.int32)
+    out = C.c_double()
+    rc = shim.qcqp_shim_onevar_qcqp(f0a.ctypes.data, fa.ctypes.data, ra.ctypes.data, len(fs), float(s), C.byref(st), C.byref(out))
+    return rc, out.value
+
+
+def test_device_intervals_match_reference(shim, golden):
+    for c in golden["intervals"]:
+        out = np.empty(4)
+        p, q, r, op = c["f"]
+        n = shim.qcqp_shim_feasible_intervals(p, q, r, orc.RELOP_CODE[op], c["s"], out.ctypes.data)
+        assert n == len(c["intervals"])
+        for i, (a, b) in enumerate(c["intervals"]):
+            assert out[2 * i] == a and out[2 * i + 1] == b
+
+
+def test_device_solver_matches_reference_goldens(shim, golden):
+    for c in golden["onevar"]:
+        st = orc.RngState.from_seed(c["seed"])
+        rc, x = _solve(shim, c["f0"], [tuple(f) for f in c["fs"]], c["s"], st)
+        if c["error"]:
+            assert rc == -2
+            continue
+        if c["result"] is None:
+            assert rc == 0, c
+        else:
+            assert rc == 1 and x == c["result"], c
+        assert st.pos == c["rng"]["pos"], c
+
+
+def test_device_solver_matches_oracle_random(shim):
+    """Wider net than the goldens: many constraints, duplicated constraints, shared endpoints, degenerate forms."""
+    rs = np.random.RandomState(2024)
+    for t in range(4000):
+        m = int(rs.randint(0, 12))
+        fs = []
+        for _ in range(m):
+            kind = rs.randint(0, 7)
+            if kind == 6:   # lattice coefficients -> exact endpoint coincidences between different constraints
+                p, q, r = float(rs.randint(-2, 3)), float(rs.randint(-2, 3)), float(rs.randint(-4, 2))
+            else:
+                p = rs.randn() * (kind != 0) * (1e-5 if kind == 5 else 1.0)
+                q = rs.randn() * (kind != 1)
+                r = rs.randn() - 1.0
+            if p == 0 and q == 0:
+                q = 1.0     # (0, 0) forms are filtered by the caller (qcqp.py:116)
+            fs.append((float(p), float(q), float(r), "==" if rs.rand() < 0.35 else "<="))
+        if m > 1 and t % 5 == 0:
+            fs[rs.randint(0, m)] = fs[rs.randint(0, m)]
+        k0 = rs.randint(0, 5)
+        f0 = (float(abs(rs.randn())) if k0 == 0 else (0.0 if k0 in (1, 2) else float(rs.randint(-2, 3))),
+              0.0 if k0 == 2 else float(rs.randint(-3, 4)) if k0 == 4 else float(rs.randn()), float(rs.randn() * 10 ** rs.randint(0, 6)))
+        s = float(rs.choice([0.0, 1e-4, 0.01, 0.3, 1.0, 2.5]) * (1 if t % 2 else abs(rs.randn())))
+        st_a = orc.RngState.from_seed(t)
+        st_b = orc.RngState.from_seed(t)
+        try:
+            want = orc.onevar_qcqp(f0, fs, s, st_a)
+            err = False
+        except OverflowError:
+            err = True
+        rc, x = _solve(shim, f0, fs, s, st_b)
+        if err:
+            assert rc == -2, (t, f0, fs, s)
+            continue
+        if want is None:
+            assert rc == 0, (t, f0, fs, s, x)
+        else:
+            assert rc == 1 and x == want, (t, f0, fs, s, x, want)
+        assert st_a.pos == st_b.pos, (t, f0, fs, s)
+
+
+def test_device_rng_transforms(shim):
+    for seed in (3, 99):
+        rs = np.random.RandomState(seed)
+        st = orc.RngState.from_seed(seed)
+        for t in range(2000):
+            if t % 3:
+                assert rs.uniform(-1.5, 2.25) == shim.qcqp_shim_uniform(C.byref(st), -1.5, 2.25)
+            else:
+                n = [1, 2, 3, 5, 8, 200][t % 6]
+                assert int(rs.choice(n)) == shim.qcqp_shim_choice(C.byref(st), n)

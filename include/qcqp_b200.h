@@ -107,6 +107,8 @@ typedef struct {
     int32_t sweeps_p2;
     int32_t status;         /* QCQP_RUN_* */
     int32_t ran_phase2;
+    int64_t steps_skipped;  /* phase-1 steps NOT executed: once a full sweep changes nothing (no move, no RNG draw) every
+                               later sweep of qcqp.py:110 is the same no-op, so the engine jumps to the end of the loop */
 } qcqp_cd_stats;
 
 /* kwargs of improve_admm (qcqp.py:254-259); rho is per run, see qcqp_admm_improve */

@@ -537,6 +537,7 @@ typedef struct {
     int32_t sweeps_p2;
     int32_t status;      /* ORC_OK or an ORC_ERR_* */
     int32_t ran_phase2;
+    int64_t steps_skipped; /* fast mode: phase-1 steps not executed after a no-op sweep (see below) */
 } orc_cd_stats;
 
 typedef struct {
@@ -617,6 +618,8 @@ static void cd_phase1(cd_ctx* c, const orc_problem* p, double* x, const orc_cd_p
     for (int t = 0; t < prm->num_iters; t++) {
         if (viol_last < viol_tol) break;
         st->sweeps_p1++;
+        int64_t updates_before = st->updates_p1;
+        int broke = 0;
         for (int i = 0; i < n; i++) {
             st->steps_p1++;
             long cnt = collect_onevar(c, p, x, i, prm->fast, 0, NULL);
@@ -642,11 +645,18 @@ static void cd_phase1(cd_ctx* c, const orc_problem* p, double* x, const orc_cd_p
                 st->updates_p1++;
             } else {
                 update_counter++;
-                if (update_counter == n) break; /* 'failed': leaves the inner loop only (qcqp.py:138-141) */
+                if (update_counter == n) { broke = 1; break; } /* 'failed': leaves the inner loop only (qcqp.py:138-141) */
             }
         }
         if (prm->fast) refresh_fval(c, p, x);
         viol_last = max_violation_ctx(c, p, x, prm->fast);
+        if (prm->fast && !broke && st->updates_p1 == updates_before && !(viol_last < viol_tol)) {
+            /* A full sweep that moved nothing drew no random number either (a feasible probe always moves), and
+               update_counter is already past n: every remaining iteration of qcqp.py:110 repeats it exactly.
+               Jump to the end of the loop; the steps not executed are reported, not counted as work. */
+            st->steps_skipped += (int64_t)(prm->num_iters - (t + 1)) * n;
+            break;
+        }
     }
 }
 

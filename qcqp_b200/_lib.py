@@ -38,7 +38,8 @@ class CdParams(C.Structure):
 
 class CdStats(C.Structure):
     _fields_ = [("steps_p1", C.c_int64), ("steps_p2", C.c_int64), ("updates_p1", C.c_int64), ("updates_p2", C.c_int64),
-                ("sweeps_p1", C.c_int32), ("sweeps_p2", C.c_int32), ("status", C.c_int32), ("ran_phase2", C.c_int32)]
+                ("sweeps_p1", C.c_int32), ("sweeps_p2", C.c_int32), ("status", C.c_int32), ("ran_phase2", C.c_int32),
+                ("steps_skipped", C.c_int64)]
 
 
 class AdmmParams(C.Structure):

@@ -55,31 +55,27 @@ enum { PH_P1 = 0, PH_P2 = 1, PH_DONE = 2 };
 // ---------------------------------------------------------------------------------------------------------
 // row dots
 // ---------------------------------------------------------------------------------------------------------
-// sparse row of incidence e against z = x with x_k := 0 (the stored row has no diagonal entry)
-__device__ __forceinline__ double sparse_row_dot_seq(const PackView& P, int e, const double* x)
+// dense row (length n, staged in the smem ring) against z: the caller has stored 0 at x[k], so z == x here.
+// Both arrays are 16-byte aligned in shared memory; lanes own consecutive pairs (LDS.128).
+__device__ __forceinline__ double dense_row_dot_warp(const double* row, const double* x, int n, int lane)
 {
-    double s = 0.0;
-    for (int t = P.row_ptr[e]; t < P.row_ptr[e + 1]; t++) s = s + P.row_val[t] * x[P.row_col[t]];
-    return s;
-}
-__device__ __forceinline__ double sparse_row_dot_warp(const PackView& P, int e, const double* x, int lane)
-{
-    double s = 0.0;
-    for (int t = P.row_ptr[e] + lane; t < P.row_ptr[e + 1]; t += 32) s = fma(P.row_val[t], x[P.row_col[t]], s);
-    return warp_sum(s);
-}
-// dense row (length n, staged in smem or read from global) against z
-__device__ __forceinline__ double dense_row_dot_warp(const double* row, const double* x, int n, int k, int lane)
-{
+    __builtin_assume(__isShared(row));
+    __builtin_assume(__isShared(x));
+    const double2* r2 = reinterpret_cast<const double2*>(row);
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    const int n2 = n >> 1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int c = lane;
-    for (; c + 96 < n; c += 128) {
-        s0 = fma(row[c], (c == k) ? 0.0 : x[c], s0);
-        s1 = fma(row[c + 32], (c + 32 == k) ? 0.0 : x[c + 32], s1);
-        s2 = fma(row[c + 64], (c + 64 == k) ? 0.0 : x[c + 64], s2);
-        s3 = fma(row[c + 96], (c + 96 == k) ? 0.0 : x[c + 96], s3);
+    int i = lane;
+    for (; i + 32 < n2; i += 64) {
+        const double2 a = r2[i], xa = x2[i], c = r2[i + 32], xc = x2[i + 32];
+        s0 = fma(a.x, xa.x, s0); s1 = fma(a.y, xa.y, s1);
+        s2 = fma(c.x, xc.x, s2); s3 = fma(c.y, xc.y, s3);
     }
-    for (; c < n; c += 32) s0 = fma(row[c], (c == k) ? 0.0 : x[c], s0);
+    if (i < n2) {
+        const double2 a = r2[i], xa = x2[i];
+        s0 = fma(a.x, xa.x, s0); s1 = fma(a.y, xa.y, s1);
+    }
+    if ((n & 1) && lane == 0) s2 = fma(row[n - 1], x[n - 1], s2);
     return warp_sum((s0 + s1) + (s2 + s3));
 }
 __device__ __forceinline__ double dense_row_dot_seq(const double* row, const double* x, int n, int k)
@@ -116,47 +112,12 @@ __device__ __forceinline__ void bitonic_sort_events(double* key, int* del, int N
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// onevar_qcqp(f0, nfs, s) for the mk constraint coefficients in scratch.  Warp-uniform return: 1 found / 0 None.
-// xout and err are valid in every lane; the RNG advances in lane 0 only.
+// tail of onevar_qcqp once the explicit (two-interval) events sit in w.evk/w.evd[0..nev): sentinels + fold, sort,
+// sweep line, minimiser.  Lane 0 owns the RNG.  Returns found (warp-uniform); xout/err valid in every lane.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int solve_level(const WarpMem& w, int mk, double s, double p0, double q0, double r0, MtRng& rng,
-                                           int evN, int lane, double* xout, int* err)
+__device__ __forceinline__ int solve_tail_sorted(const WarpMem& w, const Fold& f, int nev, double p0, double q0, double r0, MtRng& rng,
+                                                 int lane, double* xout, int* err)
 {
-    Fold f;
-    f.init();
-    if (lane == 0) w.misc[0] = 0;
-    __syncwarp();
-    for (int i = lane; i < mk; i += 32) {
-        double p = w.scp[i], q = w.scq[i];
-        if (p == 0.0 && q == 0.0) continue;   // nfs filter of qcqp.py:116,166
-        f.mcnt++;
-        Ival I[2];
-        int c = feasible_intervals(p, q, w.scr[i], w.screl[i], s, I);
-        if (c == 0) f.nempty++;
-        else if (c == 1) f.add_single(I[0].lo, I[0].hi);
-        else {
-            int at = atomicAdd(&w.misc[0], 4);
-            w.evk[at] = I[0].lo; w.evd[at] = +1;
-            w.evk[at + 1] = I[0].hi; w.evd[at + 1] = -1;
-            w.evk[at + 2] = I[1].lo; w.evd[at + 2] = +1;
-            w.evk[at + 3] = I[1].hi; w.evd[at + 3] = -1;
-        }
-    }
-    if (mk > 1) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double L2 = __shfl_xor_sync(FULL, f.L, o), H2 = __shfl_xor_sync(FULL, f.H, o);
-            int mu2 = __shfl_xor_sync(FULL, f.mu, o), m12 = __shfl_xor_sync(FULL, f.m1, o);
-            int mc2 = __shfl_xor_sync(FULL, f.mcnt, o), ne2 = __shfl_xor_sync(FULL, f.nempty, o);
-            f.merge(L2, H2, mu2, m12, mc2, ne2);
-        }
-    } else {
-        f.L = bcast(f.L, 0); f.H = bcast(f.H, 0); f.mu = bcast_i(f.mu, 0); f.m1 = bcast_i(f.m1, 0);
-        f.mcnt = bcast_i(f.mcnt, 0); f.nempty = bcast_i(f.nempty, 0);
-    }
-    __syncwarp();
-    if (f.nempty > 0) return 0;   // some constraint has no feasible point at this level: the total never reaches m + 1
-    int nev = w.misc[0];
     int found = 0, e = 0;
     double xv = 0.0;
     if (nev + 4 <= CD_SMALL_EVENTS) {
@@ -185,6 +146,141 @@ __device__ __forceinline__ int solve_level(const WarpMem& w, int mk, double s, d
     return bcast_i(found, 0);
 }
 
+__device__ __forceinline__ void fold_allreduce(Fold& f)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double L2 = __shfl_xor_sync(FULL, f.L, o), H2 = __shfl_xor_sync(FULL, f.H, o);
+        int mu2 = __shfl_xor_sync(FULL, f.mu, o), m12 = __shfl_xor_sync(FULL, f.m1, o);
+        int mc2 = __shfl_xor_sync(FULL, f.mcnt, o), ne2 = __shfl_xor_sync(FULL, f.nempty, o);
+        f.merge(L2, H2, mu2, m12, mc2, ne2);
+    }
+}
+__device__ __forceinline__ void fold_bcast(Fold& f, int src)
+{
+    f.L = bcast(f.L, src); f.H = bcast(f.H, src); f.mu = bcast_i(f.mu, src); f.m1 = bcast_i(f.m1, src);
+    f.mcnt = bcast_i(f.mcnt, src); f.nempty = bcast_i(f.nempty, src);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// onevar_qcqp, general path: the mk constraint coefficients are in scratch (any mk).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int solve_level(const WarpMem& w, int mk, double s, double p0, double q0, double r0, MtRng& rng,
+                                           int lane, double* xout, int* err)
+{
+    *err = 0;
+    *xout = 0.0;
+    Fold f;
+    f.init();
+    if (lane == 0) w.misc[0] = 0;
+    __syncwarp();
+    for (int i = lane; i < mk; i += 32) {
+        double p = w.scp[i], q = w.scq[i];
+        if (p == 0.0 && q == 0.0) continue;   // nfs filter of qcqp.py:116,166
+        f.mcnt++;
+        Ival I[2];
+        int c = feasible_intervals(p, q, w.scr[i], w.screl[i], s, I);
+        if (c == 0) f.nempty++;
+        else if (c == 1) f.add_single(I[0].lo, I[0].hi);
+        else {
+            int at = atomicAdd(&w.misc[0], 4);
+            w.evk[at] = I[0].lo; w.evd[at] = +1;
+            w.evk[at + 1] = I[0].hi; w.evd[at + 1] = -1;
+            w.evk[at + 2] = I[1].lo; w.evd[at + 2] = +1;
+            w.evk[at + 3] = I[1].hi; w.evd[at + 3] = -1;
+        }
+    }
+    fold_allreduce(f);
+    __syncwarp();
+    if (f.nempty > 0) return 0;   // some constraint has no feasible point at this level: the total never reaches m + 1
+    return solve_tail_sorted(w, f, w.misc[0], p0, q0, r0, rng, lane, xout, err);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// onevar_qcqp, register path: at most one constraint per lane (coordinates with <= 32 incident forms).
+// The feasible set of a lane's constraint is memoised on (p, q, r, s, relop): in phase 2 of a Boolean problem every
+// coordinate presents the same x_k^2 = 1 at the same frozen level, so the sqrt/div chain runs once per restart.
+// ---------------------------------------------------------------------------------------------------------
+struct IvMemo {
+    double p, q, r, s;
+    int rel, c;
+    Ival I0, I1;
+};
+// warp-uniform: the pieces in w.clo/w.chi are those of lane `src`'s memoised constraint standing alone
+struct PieceCache {
+    bool valid;
+    int src, nC;
+};
+
+__device__ __forceinline__ int solve_small(const WarpMem& w, bool active, double p, double q, double r, int rel, double s, double p0,
+                                           double q0, double r0, IvMemo& memo, PieceCache& pc, MtRng& rng, int lane, double* xout, int* err)
+{
+    *err = 0;
+    *xout = 0.0;
+    Fold f;
+    f.init();
+    int c = 0;
+    Ival I[2];
+    I[0].lo = I[0].hi = I[1].lo = I[1].hi = 0.0;
+    const bool counted = active && !(p == 0.0 && q == 0.0);   // nfs filter of qcqp.py:116,166
+    bool hit = false;
+    if (counted) {
+        if (memo.c >= 0 && memo.p == p && memo.q == q && memo.r == r && memo.s == s && memo.rel == rel) {
+            c = memo.c; I[0] = memo.I0; I[1] = memo.I1;
+            hit = true;
+        } else {
+            c = feasible_intervals(p, q, r, rel, s, I);
+            memo.p = p; memo.q = q; memo.r = r; memo.s = s; memo.rel = rel; memo.c = c; memo.I0 = I[0]; memo.I1 = I[1];
+        }
+        f.mcnt = 1;
+        if (c == 0) f.nempty = 1;
+        else if (c == 1) f.add_single(I[0].lo, I[0].hi);
+    }
+    const unsigned act = __ballot_sync(FULL, counted);
+    const unsigned two = __ballot_sync(FULL, counted && c == 2);
+    const int nact = __popc(act);
+    const int only = __ffs(act) - 1;
+    // a single counted constraint whose feasible set is memoised: the pieces of the previous call are still in place
+    const bool reuse = (nact == 1) && pc.valid && pc.src == only && (__ballot_sync(FULL, hit) & act) != 0;
+    if (!reuse) {
+        if (nact > 1) fold_allreduce(f);
+        else if (nact == 1) fold_bcast(f, only);
+        if (f.nempty > 0) { pc.valid = false; return 0; }
+    }
+    const int ntwo = __popc(two);
+    if (reuse || ntwo <= 1) {
+        if (!reuse) {
+            Ival T0 = I[0], T1 = I[1];
+            if (ntwo == 1) {
+                const int src = __ffs(two) - 1;
+                T0.lo = bcast(I[0].lo, src); T0.hi = bcast(I[0].hi, src);
+                T1.lo = bcast(I[1].lo, src); T1.hi = bcast(I[1].hi, src);
+            }
+            int nC = 0;
+            if (lane == 0) nC = sweep_small8(f, ntwo == 1, T0, T1, w.clo, w.chi);
+            pc.nC = bcast_i(nC, 0);
+            pc.valid = (nact == 1);
+            pc.src = only;
+        }
+        int found = 0, e = 0;
+        double xv = 0.0;
+        if (lane == 0) found = choose_point(p0, q0, r0, w.clo, w.chi, pc.nC, rng, &xv, &e);
+        *xout = bcast(xv, 0);
+        *err = bcast_i(e, 0);
+        return bcast_i(found, 0);
+    }
+    pc.valid = false;
+    if (counted && c == 2) {
+        const int at = 4 * __popc(two & ((1u << lane) - 1u));
+        w.evk[at] = I[0].lo; w.evd[at] = +1;
+        w.evk[at + 1] = I[0].hi; w.evd[at + 1] = -1;
+        w.evk[at + 2] = I[1].lo; w.evd[at + 2] = +1;
+        w.evk[at + 3] = I[1].hi; w.evd[at + 3] = -1;
+    }
+    __syncwarp();
+    return solve_tail_sorted(w, f, 4 * ntwo, p0, q0, r0, rng, lane, xout, err);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // cached f_j(x) from scratch; returns max constraint violation (warp-uniform)
 // ---------------------------------------------------------------------------------------------------------
@@ -201,10 +297,40 @@ __device__ __forceinline__ double refresh_fvals(const PackView& P, const WarpMem
     return warp_max(mv);
 }
 
+// per-lane metadata of one incidence, prefetched one coordinate ahead
+struct Meta {
+    uint32_t fw;
+    int rbeg, rlen;
+    double t2, qk;
+};
+__device__ __forceinline__ Meta load_meta(const PackView& P, int e, bool valid)
+{
+    Meta mt;
+    mt.fw = 0xffffffffu; mt.rbeg = 0; mt.rlen = 0; mt.t2 = 0.0; mt.qk = 0.0;
+    if (valid) {
+        mt.fw = P.inc_form[e]; mt.rbeg = P.inc_rbeg[e]; mt.rlen = P.inc_rlen[e];
+        mt.t2 = P.inc_t2[e]; mt.qk = P.inc_qk[e];
+    }
+    return mt;
+}
+
+__device__ __forceinline__ double sparse_dot_seq(const PackView& P, int rbeg, int rlen, const double* x)
+{
+    double s = 0.0;
+    for (int t = rbeg; t < rbeg + rlen; t++) s = s + P.row_val[t] * x[P.row_col[t]];
+    return s;
+}
+__device__ __forceinline__ double sparse_dot_warp(const PackView& P, int rbeg, int rlen, const double* x, int lane)
+{
+    double s = 0.0;
+    for (int t = rbeg + lane; t < rbeg + rlen; t += 32) s = fma(P.row_val[t], x[P.row_col[t]], s);
+    return warp_sum(s);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-__global__ void cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __restrict__ X0, int R, qcqp_rng_state* rngs,
+__global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __restrict__ X0, int R, qcqp_rng_state* rngs,
                           double* __restrict__ X, double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out,
                           double* ws_fval, double* ws_scr, int* ws_screl)
 {
@@ -275,7 +401,7 @@ __global__ void cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __res
     rng.pos = 624;
     int phase = PH_DONE;
     qcqp_cd_stats st;
-    st.steps_p1 = st.steps_p2 = st.updates_p1 = st.updates_p2 = 0;
+    st.steps_p1 = st.steps_p2 = st.updates_p1 = st.updates_p2 = st.steps_skipped = 0;
     st.sweeps_p1 = st.sweeps_p2 = 0; st.status = QCQP_RUN_OK; st.ran_phase2 = 0;
 
     if (live) {
@@ -294,6 +420,11 @@ __global__ void cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __res
     double viol_p2 = 0.0;         // phase 2: frozen at entry (qcqp.py:157)
     bool p1_over = live && !prm.phase1;
     unsigned slot = 0;
+    PieceCache pc;
+    pc.valid = false; pc.src = 0; pc.nC = 0;
+    IvMemo memo;
+    memo.c = -1; memo.p = memo.q = memo.r = memo.s = 0.0; memo.rel = 0;
+    memo.I0.lo = memo.I0.hi = memo.I1.lo = memo.I1.hi = 0.0;
 
     for (;;) {
         // ---------------- sweep boundary: phase transitions (warp-uniform) ----------------
@@ -315,12 +446,27 @@ __global__ void cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __res
         if (phase == PH_P1) st.sweeps_p1++;
         if (phase == PH_P2) st.sweeps_p2++;
         bool skip = false;   // phase 1 'failed' break: the rest of this sweep is not executed (qcqp.py:138-141)
+        const long long upd_before = st.updates_p1;
 
-        int nx_beg = P.inc_ptr[0], nx_end = P.inc_ptr[1];
+        // incidence ranges and per-lane metadata run one coordinate ahead of the work
+        int pb0 = P.inc_ptr[0], pb1 = P.inc_ptr[1], pb2 = P.inc_ptr[n >= 2 ? 2 : 1];
+        Meta pf = load_meta(P, pb0 + lane, pb0 + lane < pb1);
         for (int k = 0; k < n; k++, slot++) {
-            const int beg = nx_beg, end = nx_end;
-            if (k + 1 < n) { nx_beg = end; nx_end = P.inc_ptr[k + 2]; }
+            const Meta cur = pf;
+            const int beg = pb0, end = pb1;
+            pb0 = pb1; pb1 = pb2;
+            if (k + 3 <= n) pb2 = P.inc_ptr[k + 3];
+            pf = load_meta(P, pb0 + lane, (k + 1 < n) && (pb0 + lane < pb1));
+
             const bool work = (phase != PH_DONE) && !skip;
+            // z = x with x_k := 0 (utilities.py:100-101): park x_k in a register and zero it in place for this step
+            double xk = 0.0;
+            if (work) {
+                xk = w.x[k];
+                __syncwarp();
+                if (lane == 0) w.x[k] = 0.0;
+                __syncwarp();
+            }
             // ---- dense rows of this coordinate: dot each against z ----
             if (ring) {
                 const int sg = slot % S;
@@ -329,7 +475,7 @@ __global__ void cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __res
                     const double* rows = ringbuf + (size_t)sg * nd * ld;
                     if (!strict) {
                         for (int d = (phase == PH_P1 && P.dense_form[0] == 0) ? 1 : 0; d < nd; d++) {
-                            double v = dense_row_dot_warp(rows + (size_t)d * ld, w.x, n, k, lane);
+                            double v = dense_row_dot_warp(rows + (size_t)d * ld, w.x, n, lane);
                             if (lane == 0) w.dd[d] = v;
                         }
                     } else {
@@ -343,123 +489,207 @@ __global__ void cd_kernel(PackView P, CdK prm, CdLayout lay, const double* __res
                 if (!ring) break;
                 continue;
             }
-            const double xk = w.x[k];
-            // ---- one-variable coefficients of the incident forms (get_onevar_func, utilities.py:99-105) ----
-            const bool has_obj = (end > beg) && ((P.inc_form[beg] & INC_FORM_MASK) == 0);
-            const int cbeg = beg + (has_obj ? 1 : 0);
+            const int cnt = end - beg;
+            double new_xi = xk;
+            bool move = false;
+            bool dead = false;   // the reference would have raised: stop this restart, leave x as it was
+
+            if (cnt <= 32) {
+                // ======================= register path: one incidence per lane =======================
+                const bool valid = lane < cnt;
+                const int form = (int)(cur.fw & INC_FORM_MASK);
+                const bool is_obj = valid && form == 0;
+                const bool has_obj = __ballot_sync(FULL, is_obj) != 0;   // the objective, when incident, is lane 0
+                const bool need = valid && !(phase == PH_P1 && is_obj);
+                double dot = 0.0;
+                bool deferred = false;
+                if (need) {
+                    if (cur.rlen < 0) dot = w.dd[cur.rbeg];
+                    else if (strict || cur.rlen <= CD_LONG_ROW) dot = sparse_dot_seq(P, cur.rbeg, cur.rlen, w.x);
+                    else deferred = true;
+                }
+                unsigned coop = __ballot_sync(FULL, deferred);
+                while (coop) {
+                    const int src = __ffs(coop) - 1;
+                    coop &= coop - 1;
+                    double v = sparse_dot_warp(P, bcast_i(cur.rbeg, src), bcast_i(cur.rlen, src), w.x, lane);
+                    if (lane == src) dot = v;
+                }
+                // (t2, t1, t0) of get_onevar_func (utilities.py:99-105); t0 from the cached f_j(x)
+                const double cp = cur.t2;
+                const double cq = 2 * dot + cur.qk;
+                const double cr = need ? (w.fval[form] - xk * (cp * xk + cq)) : 0.0;
+                const int crel = (int)((cur.fw >> INC_RELOP_SHIFT) & 3);
+                const bool active = valid && !is_obj;
+                double p0 = 0.0, q0 = 0.0, r0 = 0.0;
+                if (phase == PH_P2) {
+                    if (has_obj) { p0 = bcast(cp, 0); q0 = bcast(cq, 0); r0 = bcast(cr, 0); }
+                    else r0 = w.fval[0];
+                }
+                if (phase == PH_P1) {
+                    // ---- phase 1: bisect the violation level (qcqp.py:113-141) ----
+                    st.steps_p1++;
+                    const bool nz = active && !(cp == 0.0 && cq == 0.0);
+                    if (__ballot_sync(FULL, nz) == 0) { st.status = QCQP_RUN_EMPTY_MAX; dead = true; }
+                    else {
+                        const double viol = warp_max(nz ? violation_of(crel, onevar_eval(cp, cq, cr, xk)) : -QCQP_INF);
+                        double new_viol = viol;
+                        double ss = -tol, es = viol - viol_tol;
+                        while (es - ss > tol) {
+                            const double s = (ss + es) / 2;
+                            double xi;
+                            int err;
+                            int ok = solve_small(w, active, cp, cq, cr, crel, s, 0.0, 0.0, 0.0, memo, pc, rng, lane, &xi, &err);
+                            if (err) { st.status = err; dead = true; break; }
+                            if (!ok) ss = s;
+                            else { new_xi = xi; new_viol = s; es = s; }
+                        }
+                        if (!dead) {
+                            if (new_viol < viol) { move = true; update_counter = 0; st.updates_p1++; }
+                            else {
+                                update_counter++;
+                                if (update_counter == n) skip = true;
+                            }
+                        }
+                    }
+                } else {
+                    // ---- phase 2: minimise the objective at the frozen level (qcqp.py:162-176) ----
+                    st.steps_p2++;
+                    double xi;
+                    int err;
+                    int ok = solve_small(w, active, cp, cq, cr, crel, viol_p2, p0, q0, r0, memo, pc, rng, lane, &xi, &err);
+                    if (err) { st.status = err; dead = true; }
+                    else if (ok && fabs(xi - xk) > tol) { move = true; new_xi = xi; update_counter = 0; st.updates_p2++; }
+                    else {
+                        update_counter++;
+                        if (update_counter == n) phase = PH_DONE;   // converged
+                    }
+                }
+                // f_j(x) = t0 + b (t2 b + t1) for every incident form; x_k back in place (moved or not)
+                if (move && need) w.fval[form] = cr + new_xi * (cp * new_xi + cq);
+                if (lane == 0) w.x[k] = new_xi;
+                if (dead) phase = PH_DONE;
+                __syncwarp();
+                continue;
+            }
+            pc.valid = false;   // the general path reuses the piece buffers
+
+            // ======================= general path: coefficients through scratch (any count) =======================
+            const bool has_obj = (cur.fw & INC_FORM_MASK) == 0 && lane == 0;
+            const bool obj_inc = __ballot_sync(FULL, has_obj) != 0;
+            const int cbeg = beg + (obj_inc ? 1 : 0);
             const int mk = end - cbeg;
             double p0 = 0.0, q0 = 0.0, r0 = 0.0;
             if (phase == PH_P2) {
                 r0 = w.fval[0];
-                if (has_obj) {
-                    uint32_t fw = P.inc_form[beg];
+                if (obj_inc) {
+                    const int orb = bcast_i(cur.rbeg, 0), orl = bcast_i(cur.rlen, 0);
                     double dot;
-                    if (fw & INC_DENSE_BIT) dot = w.dd[P.dense_slot[0]];
-                    else if (strict) dot = sparse_row_dot_seq(P, beg, w.x);
-                    else dot = sparse_row_dot_warp(P, beg, w.x, lane);
-                    p0 = P.inc_t2[beg];
-                    q0 = 2 * dot + P.inc_qk[beg];
+                    if (orl < 0) dot = w.dd[orb];
+                    else if (strict) dot = sparse_dot_seq(P, orb, orl, w.x);
+                    else dot = sparse_dot_warp(P, orb, orl, w.x, lane);
+                    p0 = bcast(cur.t2, 0);
+                    q0 = 2 * dot + bcast(cur.qk, 0);
                     r0 = w.fval[0] - xk * (p0 * xk + q0);
                 }
             }
             for (int base = 0; base < mk; base += 32) {
                 const int i = base + lane;
                 const bool mine = i < mk;
-                const int e = cbeg + (mine ? i : 0);
-                uint32_t fw = 0;
+                const Meta mt = load_meta(P, cbeg + i, mine);
                 double dot = 0.0;
                 bool deferred = false;
                 if (mine) {
-                    fw = P.inc_form[e];
-                    if (fw & INC_DENSE_BIT) dot = w.dd[P.dense_slot[fw & INC_FORM_MASK]];
-                    else if (strict || P.row_ptr[e + 1] - P.row_ptr[e] <= CD_LONG_ROW) dot = sparse_row_dot_seq(P, e, w.x);
+                    if (mt.rlen < 0) dot = w.dd[mt.rbeg];
+                    else if (strict || mt.rlen <= CD_LONG_ROW) dot = sparse_dot_seq(P, mt.rbeg, mt.rlen, w.x);
                     else deferred = true;
                 }
                 unsigned coop = __ballot_sync(FULL, deferred);
                 while (coop) {
-                    int src = __ffs(coop) - 1;
+                    const int src = __ffs(coop) - 1;
                     coop &= coop - 1;
-                    double v = sparse_row_dot_warp(P, cbeg + base + src, w.x, lane);
+                    double v = sparse_dot_warp(P, bcast_i(mt.rbeg, src), bcast_i(mt.rlen, src), w.x, lane);
                     if (lane == src) dot = v;
                 }
                 if (mine) {
-                    const int j = fw & INC_FORM_MASK;
-                    const double t2 = P.inc_t2[e];
-                    const double t1 = 2 * dot + P.inc_qk[e];
-                    w.scp[i] = t2;
+                    const int j = (int)(mt.fw & INC_FORM_MASK);
+                    const double t1 = 2 * dot + mt.qk;
+                    w.scp[i] = mt.t2;
                     w.scq[i] = t1;
-                    w.scr[i] = w.fval[j] - xk * (t2 * xk + t1);
-                    w.screl[i] = (fw >> INC_RELOP_SHIFT) & 3;
+                    w.scr[i] = w.fval[j] - xk * (mt.t2 * xk + t1);
+                    w.screl[i] = (int)((mt.fw >> INC_RELOP_SHIFT) & 3);
                 }
             }
             __syncwarp();
-
-            double new_xi = xk;
-            bool move = false;
             if (phase == PH_P1) {
-                // ---- phase 1: bisect the violation level (qcqp.py:113-141) ----
                 st.steps_p1++;
                 double vmax = -QCQP_INF;
-                int cnt = 0;
+                int cz = 0;
                 for (int i = lane; i < mk; i += 32) {
                     double p = w.scp[i], q = w.scq[i];
                     if (p == 0.0 && q == 0.0) continue;
-                    cnt++;
+                    cz++;
                     double v = violation_of(w.screl[i], onevar_eval(p, q, w.scr[i], xk));
                     vmax = (v > vmax) ? v : vmax;
                 }
-                cnt = warp_sum_i(cnt);
-                if (cnt == 0) { st.status = QCQP_RUN_EMPTY_MAX; phase = PH_DONE; continue; }
-                const double viol = warp_max(vmax);
-                double new_viol = viol;
-                double ss = -tol, es = viol - viol_tol;
-                while (es - ss > tol) {
-                    double s = (ss + es) / 2;
-                    double xi;
-                    int err;
-                    int ok = solve_level(w, mk, s, 0.0, 0.0, 0.0, rng, lay.evN, lane, &xi, &err);
-                    if (err) { st.status = err; break; }
-                    if (!ok) ss = s;
-                    else { new_xi = xi; new_viol = s; es = s; }
-                }
-                if (st.status != QCQP_RUN_OK) { phase = PH_DONE; continue; }
-                if (new_viol < viol) { move = true; update_counter = 0; st.updates_p1++; }
+                cz = warp_sum_i(cz);
+                if (cz == 0) { st.status = QCQP_RUN_EMPTY_MAX; dead = true; }
                 else {
-                    update_counter++;
-                    if (update_counter == n) skip = true;
+                    const double viol = warp_max(vmax);
+                    double new_viol = viol;
+                    double ss = -tol, es = viol - viol_tol;
+                    while (es - ss > tol) {
+                        const double s = (ss + es) / 2;
+                        double xi;
+                        int err;
+                        int ok = solve_level(w, mk, s, 0.0, 0.0, 0.0, rng, lane, &xi, &err);
+                        if (err) { st.status = err; dead = true; break; }
+                        if (!ok) ss = s;
+                        else { new_xi = xi; new_viol = s; es = s; }
+                    }
+                    if (!dead) {
+                        if (new_viol < viol) { move = true; update_counter = 0; st.updates_p1++; }
+                        else {
+                            update_counter++;
+                            if (update_counter == n) skip = true;
+                        }
+                    }
                 }
             } else {
-                // ---- phase 2: minimise the objective at the frozen level (qcqp.py:162-176) ----
                 st.steps_p2++;
                 double xi;
                 int err;
-                int ok = solve_level(w, mk, viol_p2, p0, q0, r0, rng, lay.evN, lane, &xi, &err);
-                if (err) { st.status = err; phase = PH_DONE; continue; }
-                if (ok && fabs(xi - xk) > tol) { move = true; new_xi = xi; update_counter = 0; st.updates_p2++; }
+                int ok = solve_level(w, mk, viol_p2, p0, q0, r0, rng, lane, &xi, &err);
+                if (err) { st.status = err; dead = true; }
+                else if (ok && fabs(xi - xk) > tol) { move = true; new_xi = xi; update_counter = 0; st.updates_p2++; }
                 else {
                     update_counter++;
                     if (update_counter == n) phase = PH_DONE;   // converged
                 }
             }
             if (move) {
-                // f_j(x) = t0 + b (t2 b + t1) for every incident form
                 const double b = new_xi;
                 for (int i = lane; i < mk; i += 32) {
-                    int j = P.inc_form[cbeg + i] & INC_FORM_MASK;
+                    int j = (int)(P.inc_form[cbeg + i] & INC_FORM_MASK);
                     w.fval[j] = w.scr[i] + b * (w.scp[i] * b + w.scq[i]);
                 }
-                if (lane == 0) {
-                    if (phase != PH_P1 && has_obj) w.fval[0] = r0 + b * (p0 * b + q0);
-                    w.x[k] = b;
-                }
-                __syncwarp();
+                if (lane == 0 && phase != PH_P1 && obj_inc) w.fval[0] = r0 + b * (p0 * b + q0);
             }
+            if (lane == 0) w.x[k] = new_xi;
+            if (dead) phase = PH_DONE;
+            __syncwarp();
         }
         // ---------------- end of sweep ----------------
         if (phase == PH_P1) {
             double mv = refresh_fvals(P, w, 1, strict, lane);   // viol = max(prob.violations(x))  (qcqp.py:142)
             viol_last = mv;
             t++;
+            if (!skip && st.updates_p1 == upd_before && !(viol_last < viol_tol) && t < prm.num_iters) {
+                // A full sweep that moved nothing drew no random number either (a feasible probe always moves) and
+                // update_counter is past n, so every remaining iteration of qcqp.py:110 would repeat it exactly.
+                st.steps_skipped += (long long)(prm.num_iters - t) * n;
+                t = prm.num_iters;
+            }
         } else if (phase == PH_P2) {
             t++;
             if (prm.refresh_every > 0 && (t % prm.refresh_every) == 0) refresh_fvals(P, w, 0, strict, lane);
@@ -522,7 +752,7 @@ static int plan_layout(const qcqp_pack* p, int R, CdLayout* L)
         if (fixed + l.warp_stride > (unsigned)smem_max)
             return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: one restart plus the dense-row ring exceeds shared memory");
         int wmax = (int)((smem_max - fixed) / l.warp_stride);
-        if (wmax > 15) wmax = 15;
+        if (wmax > 7) wmax = 7;   // 7 restart warps + the producer = 256 threads, 255 registers each
         W = (R + sms - 1) / sms;          // spread the restarts over all SMs first, then share rows inside a CTA
         if (W < 1) W = 1;
         if (W > wmax) W = wmax;

@@ -32,8 +32,8 @@ int fail(int code, const std::string& msg);
 //   coordinate-major incidence, for the CD sweep:
 //     inc_ptr[n+1]; for incidence e in [inc_ptr[k], inc_ptr[k+1]):  (forms in ascending j; objective first)
 //       inc_form[e]  = j | relop_j << 28 | dense << 31     inc_t2[e] = P_j[k,k]     inc_qk[e] = q_j[k]
-//       off-diagonal entries of row k of P_j: row_col/row_val[row_ptr[e] .. row_ptr[e+1])  (sorted by column;
-//       empty for forms stored dense)
+//       off-diagonal entries of row k of P_j: row_col/row_val[inc_rbeg[e] .. inc_rbeg[e] + inc_rlen[e])  (sorted by
+//       column); for a form stored dense inc_rlen[e] = -1 and inc_rbeg[e] = its dense slot
 //   form-major COO, for f_j(x) from scratch:
 //     f_ptr[m+2]; entries (f_row, f_col, f_val) sorted by (row, col);  q_ptr[m+2]; (q_idx, q_val); r[m+1]; relop[m+1]
 //   dense forms: dense_P[slot][n][ld] row-major, ld = n rounded up to even (16-byte rows for cp.async.bulk)
@@ -50,7 +50,8 @@ struct PackView {
     const uint32_t* inc_form;
     const double* inc_t2;
     const double* inc_qk;
-    const int* row_ptr;
+    const int* inc_rbeg;
+    const int* inc_rlen;
     const int* row_col;
     const double* row_val;
     const long long* f_ptr;

@@ -37,13 +37,37 @@ __device__ __forceinline__ double eval_sparse_form_warp(const PackView& P, int j
     return warp_sum(acc) + P.r[j];
 }
 
-// whole warp, one dense form (fast mode): lanes own columns, rows stream from HBM/L2 coalesced
+// whole warp, one dense form (fast mode): lanes own column pairs (16-byte loads), four rows in flight per pass so
+// the loads of one pass overlap instead of queueing behind each other's L2 latency
 __device__ __forceinline__ double eval_dense_form_warp(const PackView& P, int j, const double* x, int lane)
 {
     const int n = P.n, ld = P.ld;
     const double* M = P.dense_P + (size_t)P.dense_slot[j] * n * ld;
+    const int n2 = n >> 1;
     double acc = 0.0;
-    for (int i = 0; i < n; i++) {
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const double2* r0 = reinterpret_cast<const double2*>(M + (size_t)i * ld);
+        const double2* r1 = reinterpret_cast<const double2*>(M + (size_t)(i + 1) * ld);
+        const double2* r2 = reinterpret_cast<const double2*>(M + (size_t)(i + 2) * ld);
+        const double2* r3 = reinterpret_cast<const double2*>(M + (size_t)(i + 3) * ld);
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        for (int c = lane; c < n2; c += 32) {
+            const double2 a0 = r0[c], a1 = r1[c], a2 = r2[c], a3 = r3[c];
+            const double xa = x[2 * c], xb = x[2 * c + 1];
+            p0 = fma(a0.x, xa, p0); p0 = fma(a0.y, xb, p0);
+            p1 = fma(a1.x, xa, p1); p1 = fma(a1.y, xb, p1);
+            p2 = fma(a2.x, xa, p2); p2 = fma(a2.y, xb, p2);
+            p3 = fma(a3.x, xa, p3); p3 = fma(a3.y, xb, p3);
+        }
+        if ((n & 1) && lane == 0) {
+            const double xl = x[n - 1];
+            p0 = fma(M[(size_t)i * ld + n - 1], xl, p0); p1 = fma(M[(size_t)(i + 1) * ld + n - 1], xl, p1);
+            p2 = fma(M[(size_t)(i + 2) * ld + n - 1], xl, p2); p3 = fma(M[(size_t)(i + 3) * ld + n - 1], xl, p3);
+        }
+        acc = fma(p0, x[i], acc); acc = fma(p1, x[i + 1], acc); acc = fma(p2, x[i + 2], acc); acc = fma(p3, x[i + 3], acc);
+    }
+    for (; i < n; i++) {
         const double* row = M + (size_t)i * ld;
         double part = 0.0;
         for (int c = lane; c < n; c += 32) part = fma(row[c], x[c], part);

@@ -13,13 +13,14 @@ using namespace qcqp;
 
 // single-thread composition of the pieces the CD kernel runs per warp (cd.cu: solve_level)
 extern "C" int qcqp_shim_onevar_qcqp(const double* f0 /*p,q,r*/, const double* fs /*[m][3]*/, const int32_t* relops, int32_t m,
-                                     double s, qcqp_rng_state* st, double* xout)
+                                     double s, qcqp_rng_state* st, double* xout, int32_t force_general)
 {
     std::vector<double> ev_key(4 * (size_t)m + 8), c_lo(2 * (size_t)m + 4), c_hi(2 * (size_t)m + 4);
     std::vector<int> ev_del(4 * (size_t)m + 8);
     Fold fold;
     fold.init();
-    int nev = 0;
+    int nev = 0, ntwo = 0;
+    Ival T0{0, 0}, T1{0, 0};
     for (int i = 0; i < m; i++) {
         double p = fs[3 * i], q = fs[3 * i + 1], r = fs[3 * i + 2];
         fold.mcnt++;   // the caller has already dropped (p, q) == (0, 0) forms, as qcqp.py:116 does
@@ -28,14 +29,20 @@ extern "C" int qcqp_shim_onevar_qcqp(const double* f0 /*p,q,r*/, const double* f
         if (c == 0) fold.nempty++;
         else if (c == 1) fold.add_single(I[0].lo, I[0].hi);
         else {
+            ntwo++; T0 = I[0]; T1 = I[1];
             ev_key[nev] = I[0].lo; ev_del[nev++] = +1; ev_key[nev] = I[0].hi; ev_del[nev++] = -1;
             ev_key[nev] = I[1].lo; ev_del[nev++] = +1; ev_key[nev] = I[1].hi; ev_del[nev++] = -1;
         }
     }
     if (fold.nempty > 0) return 0;
-    nev = finish_events(fold, ev_key.data(), ev_del.data(), nev);
-    insertion_sort_events(ev_key.data(), ev_del.data(), nev);
-    int nC = sweep_sorted(ev_key.data(), ev_del.data(), nev, fold.mcnt, c_lo.data(), c_hi.data());
+    int nC;
+    if (ntwo <= 1 && !force_general) {
+        nC = sweep_small8(fold, ntwo == 1, T0, T1, c_lo.data(), c_hi.data());   // the kernel's register path
+    } else {
+        nev = finish_events(fold, ev_key.data(), ev_del.data(), nev);
+        insertion_sort_events(ev_key.data(), ev_del.data(), nev);
+        nC = sweep_sorted(ev_key.data(), ev_del.data(), nev, fold.mcnt, c_lo.data(), c_hi.data());
+    }
     MtRng rng{st->key, st->pos};
     int err = 0;
     int ok = choose_point(f0[0], f0[1], f0[2], c_lo.data(), c_hi.data(), nC, rng, xout, &err);

@@ -248,6 +248,51 @@ QCQP_HD int finish_events(const Fold& f, double* ev_key, int* ev_del, int nev)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// register-resident sweep for at most 8 events (the common case: no or one two-interval constraint):
+// Batcher's 19-comparator network, then the same merge/scan as sweep_sorted.  Pieces (at most 4) go to c_lo/c_hi.
+// ---------------------------------------------------------------------------------------------------------
+#define QCQP_CSWAP(a, b)                                                          \
+    do {                                                                          \
+        if (k[a] > k[b]) { double tk = k[a]; k[a] = k[b]; k[b] = tk; int td = d[a]; d[a] = d[b]; d[b] = td; } \
+    } while (0)
+
+QCQP_HD int sweep_small8(const Fold& f, bool has_two, const Ival& I0, const Ival& I1, double* c_lo, double* c_hi)
+{
+    double k[8];
+    int d[8];
+    k[0] = -QCQP_INF; d[0] = +1;
+    k[1] = QCQP_INF; d[1] = -1;
+    if (f.m1 > 0) { k[2] = f.L; d[2] = f.m1; k[3] = f.H; d[3] = -f.mu; }
+    else { k[2] = QCQP_INF; d[2] = 0; k[3] = QCQP_INF; d[3] = 0; }       // pads join the +inf sentinel and add 0
+    if (has_two) { k[4] = I0.lo; d[4] = +1; k[5] = I0.hi; d[5] = -1; k[6] = I1.lo; d[6] = +1; k[7] = I1.hi; d[7] = -1; }
+    else { k[4] = k[5] = k[6] = k[7] = QCQP_INF; d[4] = d[5] = d[6] = d[7] = 0; }
+    QCQP_CSWAP(0, 1); QCQP_CSWAP(2, 3); QCQP_CSWAP(4, 5); QCQP_CSWAP(6, 7);
+    QCQP_CSWAP(0, 2); QCQP_CSWAP(1, 3); QCQP_CSWAP(4, 6); QCQP_CSWAP(5, 7);
+    QCQP_CSWAP(1, 2); QCQP_CSWAP(5, 6);
+    QCQP_CSWAP(0, 4); QCQP_CSWAP(1, 5); QCQP_CSWAP(2, 6); QCQP_CSWAP(3, 7);
+    QCQP_CSWAP(2, 4); QCQP_CSWAP(3, 5);
+    QCQP_CSWAP(1, 2); QCQP_CSWAP(3, 4); QCQP_CSWAP(5, 6);
+    int nC = 0;
+    long tot = 0;
+    double prev_key = 0.0, cur_key = k[0];
+    int cur_d = d[0];
+    bool have_prev = false;
+#pragma unroll
+    for (int i = 1; i <= 8; i++) {
+        if (i < 8 && k[i] == cur_key) { cur_d += d[i]; continue; }
+        if (cur_d != 0) {
+            tot += cur_d;
+            if (tot == f.mcnt && cur_d == -1 && have_prev) { c_lo[nC] = prev_key; c_hi[nC] = cur_key; nC++; }
+            prev_key = cur_key;
+            have_prev = true;
+        }
+        if (i < 8) { cur_key = k[i]; cur_d = d[i]; }
+    }
+    return nC;
+}
+#undef QCQP_CSWAP
+
+// ---------------------------------------------------------------------------------------------------------
 // the minimiser of f0 = (p, q, r) over the pieces (utilities.py:263-288).  Returns 1 and *xout, 0 for None.
 // *err: QCQP_RUN_UNBOUNDED_UNIFORM when the reference would raise OverflowError.
 // ---------------------------------------------------------------------------------------------------------
@@ -264,6 +309,29 @@ QCQP_HD int choose_point(double p, double q, double r, const double* c_lo, const
     }
     const bool have_x0 = (p > 0.0);
     const double x0 = have_x0 ? (-q / (2. * p)) : 0.0;
+    if (nC <= 2) {
+        // register path for the common one- or two-piece feasible set: every endpoint value is computed once
+        const bool two = (nC == 2);
+        const double lo0 = c_lo[0], hi0 = c_hi[0];
+        const double lo1 = two ? c_lo[1] : 0.0, hi1 = two ? c_hi[1] : 0.0;
+        if (have_x0 && ((lo0 <= x0 && x0 <= hi0) || (two && lo1 <= x0 && x0 <= hi1))) { *xout = x0; return 1; }
+        const double v0 = onevar_eval(p, q, r, lo0), v1 = onevar_eval(p, q, r, hi0);
+        const double v2 = two ? onevar_eval(p, q, r, lo1) : QCQP_INF, v3 = two ? onevar_eval(p, q, r, hi1) : QCQP_INF;
+        double bestf = QCQP_INF;
+        if (v0 < bestf) bestf = v0;
+        if (v1 < bestf) bestf = v1;
+        if (v2 < bestf) bestf = v2;
+        if (v3 < bestf) bestf = v3;
+        const bool m0 = (v0 == bestf), m1 = (v1 == bestf), m2 = two && (v2 == bestf), m3 = two && (v3 == bestf);
+        const int cnt = (int)m0 + (int)m1 + (int)m2 + (int)m3;
+        if (cnt == 0) return 0;
+        int pick = (cnt == 1) ? 0 : rng.choice(cnt);
+        if (m0) { if (pick == 0) { *xout = lo0; return 1; } pick--; }
+        if (m1) { if (pick == 0) { *xout = hi0; return 1; } pick--; }
+        if (m2) { if (pick == 0) { *xout = lo1; return 1; } pick--; }
+        *xout = hi1;
+        return 1;
+    }
     // pass 1: the unconstrained minimiser wins as soon as a piece contains it; otherwise the smallest endpoint value
     double bestf = QCQP_INF;
     for (int i = 0; i < nC; i++) {
@@ -275,11 +343,14 @@ QCQP_HD int choose_point(double p, double q, double r, const double* c_lo, const
     }
     // pass 2: endpoints attaining it, in order (the reference's bestxs list); NaN values never match
     int cnt = 0;
+    double first = 0.0;
     for (int i = 0; i < nC; i++) {
-        if (onevar_eval(p, q, r, c_lo[i]) == bestf) cnt++;
-        if (onevar_eval(p, q, r, c_hi[i]) == bestf) cnt++;
+        double lo = c_lo[i], hi = c_hi[i];
+        if (onevar_eval(p, q, r, lo) == bestf) { if (cnt == 0) first = lo; cnt++; }
+        if (onevar_eval(p, q, r, hi) == bestf) { if (cnt == 0) first = hi; cnt++; }
     }
     if (cnt == 0) return 0;
+    if (cnt == 1) { *xout = first; return 1; }    // np.random.choice on a 1-element list draws nothing
     int pick = rng.choice(cnt);
     for (int i = 0; i < nC; i++) {
         if (onevar_eval(p, q, r, c_lo[i]) == bestf) { if (pick == 0) { *xout = c_lo[i]; return 1; } pick--; }

@@ -246,7 +246,12 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     int rc = QCQP_OK;
 #define UP(vec, field) if (rc == QCQP_OK) rc = upload(p, vec, &v.field)
     UP(inc_ptr, inc_ptr); UP(inc_form, inc_form); UP(inc_t2, inc_t2); UP(inc_qk, inc_qk);
-    UP(row_ptr, row_ptr); UP(row_col, row_col); UP(row_val, row_val);
+    std::vector<int> inc_rbeg((size_t)INC), inc_rlen((size_t)INC);
+    for (int64_t e = 0; e < INC; e++) {
+        if (inc_form[e] & INC_DENSE_BIT) { inc_rbeg[e] = dense_slot[inc_form[e] & INC_FORM_MASK]; inc_rlen[e] = -1; }
+        else { inc_rbeg[e] = row_ptr[e]; inc_rlen[e] = row_len[e]; }
+    }
+    UP(inc_rbeg, inc_rbeg); UP(inc_rlen, inc_rlen); UP(row_col, row_col); UP(row_val, row_val);
     UP(f_ptr, f_ptr); UP(f_row, f_row); UP(f_col, f_col); UP(f_val, f_val);
     UP(q_ptr, q_ptr); UP(q_idx, q_idx); UP(q_val, q_val);
     UP(r, r); UP(relop, relop); UP(dense_slot, dense_slot); UP(dense_form, dense_form); UP(dense_P, dense_P);

@@ -72,7 +72,7 @@ def test_cd_strict_matches_oracle(gen, gargs, R, kw):
     for r in range(R):
         xo, fo, vo, so, st = out[r]
         assert sg[r].status == so.status
-        assert (sg[r].steps_p1, sg[r].steps_p2) == (so.steps_p1, so.steps_p2), (r, sg[r].steps_p1, so.steps_p1, sg[r].steps_p2, so.steps_p2)
+        assert (sg[r].steps_p1, sg[r].steps_p2, sg[r].steps_skipped) == (so.steps_p1, so.steps_p2, so.steps_skipped), (r, sg[r].steps_p1, so.steps_p1, sg[r].steps_p2, so.steps_p2)
         assert rng_g[r].pos == st.pos, r
         assert rel_close(Xg[r], xo, rtol=1e-9, atol=1e-9), r
         assert rel_close(fg[r], fo, rtol=1e-9, atol=1e-9)
@@ -110,4 +110,24 @@ def test_cd_error_statuses():
     pack = engine.Pack(forms)
     X, f0, mv, st = pack.cd_improve(np.full((1, n), 3.0), engine.rng_states(seeds=[1]))
     assert st[0].status == 1
+    pack.close()
+
+
+def test_phase1_fixed_point_is_fast_forwarded():
+    """x_k^2 - 1 in (viol_tol, viol_tol + tol]: phase 1 can never move the coordinate (qcqp.py:122: the bisection loop does
+    not start), so the reference burns all num_iters sweeps as no-ops.  The engine detects the fixed point, reports the
+    steps it did not execute, and returns the same point and the same untouched RNG stream as the oracle."""
+    from oracle import oracle as orc
+    from qcqp_b200 import engine
+    forms, _ = GEN["bls"](n=12, m=18, seed=1)
+    x0 = np.ones(12)
+    x0[3] = np.sqrt(1.01005)
+    pack = engine.Pack(forms)
+    rng = engine.rng_states(seeds=[5])
+    X, f0, mv, st = pack.cd_improve(x0[None, :], rng, strict=True, num_iters=50)
+    P = orc.Problem(forms)
+    sto = orc.RngState.from_seed(5)
+    xo, so = P.improve_cd(x0, sto, fast=False, num_iters=50)    # faithful mode executes every no-op sweep
+    assert st[0].steps_skipped > 0 and st[0].steps_p1 + st[0].steps_skipped == so.steps_p1
+    assert np.array_equal(X[0], xo) and rng[0].pos == sto.pos and st[0].ran_phase2 == so.ran_phase2 == 0
     pack.close()

@@ -21,7 +21,7 @@ def shim():
         subprocess.check_call(["/usr/bin/g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", SRC, "-o", SO])
     L = C.CDLL(SO)
     L.qcqp_shim_onevar_qcqp.restype = C.c_int
-    L.qcqp_shim_onevar_qcqp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
+    L.qcqp_shim_onevar_qcqp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
     L.qcqp_shim_feasible_intervals.restype = C.c_int
     L.qcqp_shim_feasible_intervals.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_void_p]
     L.qcqp_shim_uniform.restype = C.c_double
@@ -31,12 +31,12 @@ def shim():
     return L
 
 
-def _solve(shim, f0, fs, s, st):
+def _solve(shim, f0, fs, s, st, force_general=0):
     f0a = np.ascontiguousarray(f0, dtype=np.float64)
     fa = np.ascontiguousarray([f[:3] for f in fs], dtype=np.float64).reshape(-1, 3)
     ra = np.ascontiguousarray([orc.RELOP_CODE[f[3]] for f in fs], dtype=np.int32)
     out = C.c_double()
-    rc = shim.qcqp_shim_onevar_qcqp(f0a.ctypes.data, fa.ctypes.data, ra.ctypes.data, len(fs), float(s), C.byref(st), C.byref(out))
+    rc = shim.qcqp_shim_onevar_qcqp(f0a.ctypes.data, fa.ctypes.data, ra.ctypes.data, len(fs), float(s), C.byref(st), C.byref(out), force_general)
     return rc, out.value
 
 
@@ -94,15 +94,17 @@ def test_device_solver_matches_oracle_random(shim):
             err = False
         except OverflowError:
             err = True
-        rc, x = _solve(shim, f0, fs, s, st_b)
-        if err:
-            assert rc == -2, (t, f0, fs, s)
-            continue
-        if want is None:
-            assert rc == 0, (t, f0, fs, s, x)
-        else:
-            assert rc == 1 and x == want, (t, f0, fs, s, x, want)
-        assert st_a.pos == st_b.pos, (t, f0, fs, s)
+        for force_general in (0, 1):    # register path (<= 1 two-interval constraint) and the sorted-event path
+            st_b = orc.RngState.from_seed(t)
+            rc, x = _solve(shim, f0, fs, s, st_b, force_general)
+            if err:
+                assert rc == -2, (t, f0, fs, s)
+                continue
+            if want is None:
+                assert rc == 0, (t, f0, fs, s, x)
+            else:
+                assert rc == 1 and x == want, (t, f0, fs, s, x, want)
+            assert st_a.pos == st_b.pos, (t, f0, fs, s)
 
 
 def test_device_rng_transforms(shim):

@@ -54,6 +54,7 @@ if __name__ == "__main__":
         Xg, fg, vg, sg = pack.cd_improve(X0, rng)
         dt = time.time() - t0
         steps = sum(s.steps_p1 + s.steps_p2 for s in sg)
+        print("   skipped steps", sum(s.steps_skipped for s in sg), "p1 sweeps mean", np.mean([s.sweeps_p1 for s in sg]), "stuck", sum(1 for s in sg if s.steps_skipped > 0))
         sw2 = np.mean([s.sweeps_p2 for s in sg])
         print("C2 R=%d: %.3fs wall (incl copies), total steps %d = %.1f restart-sweeps -> %.0f restart-sweeps/s; mean p2 sweeps %.1f; f0 best %.6g maxviol max %.3g"
               % (R, dt, steps, steps / 1000.0, steps / 1000.0 / dt, sw2, fg.min(), vg.max()))

@@ -27,6 +27,14 @@ struct DevBuf {
     template <class T> T* as() { return (T*)p; }
 };
 
+// carves 256-byte aligned pieces out of the pack's staging arena
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    template <class T> T* take(size_t bytes) { T* r = (T*)(base + off); off += pad(bytes); return r; }
+};
+
 static int check_pack(qcqp_pack* p, const char* who)
 {
     if (!p) return fail(QCQP_ERR_INVALID, std::string(who) + ": null pack");
@@ -54,15 +62,16 @@ extern "C" int qcqp_eval(qcqp_pack* pack, const double* X, int32_t R, double* f0
     if (R < 0 || (R > 0 && (!X || !f0 || !maxviol))) return fail(QCQP_ERR_INVALID, "qcqp_eval: bad argument");
     if (R == 0) return QCQP_OK;
     const size_t n = pack->v.n, m = pack->v.m;
-    DevBuf dX, dF, dM, dV;
-    TRY(dX.alloc(R * n * 8)); TRY(dF.alloc(R * 8)); TRY(dM.alloc(R * 8));
-    if (viol) TRY(dV.alloc(R * m * 8));
-    QCQP_CUDA_TRY(cudaMemcpy(dX.p, X, R * n * 8, cudaMemcpyHostToDevice));
-    TRY(eval_launch(pack, dX.as<double>(), R, dF.as<double>(), dM.as<double>(), viol ? dV.as<double>() : nullptr, 0));
+    TRY(ensure_io(pack, Arena::pad(R * n * 8) + 2 * Arena::pad(R * 8) + Arena::pad(viol ? R * m * 8 : 0)));
+    Arena ar; ar.base = (char*)pack->io;
+    double* dX = ar.take<double>(R * n * 8); double* dF = ar.take<double>(R * 8); double* dM = ar.take<double>(R * 8);
+    double* dV = viol ? ar.take<double>(R * m * 8) : nullptr;
+    QCQP_CUDA_TRY(cudaMemcpyAsync(dX, X, R * n * 8, cudaMemcpyHostToDevice, 0));
+    TRY(eval_launch(pack, dX, R, dF, dM, dV, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF, R * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, R * 8, cudaMemcpyDeviceToHost, 0));
+    if (viol) QCQP_CUDA_TRY(cudaMemcpyAsync(viol, dV, R * m * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaStreamSynchronize(0));
-    QCQP_CUDA_TRY(cudaMemcpy(f0, dF.p, R * 8, cudaMemcpyDeviceToHost));
-    QCQP_CUDA_TRY(cudaMemcpy(maxviol, dM.p, R * 8, cudaMemcpyDeviceToHost));
-    if (viol) QCQP_CUDA_TRY(cudaMemcpy(viol, dV.p, R * m * 8, cudaMemcpyDeviceToHost));
     return QCQP_OK;
 }
 
@@ -91,19 +100,22 @@ extern "C" int qcqp_cd_improve(qcqp_pack* pack, const qcqp_cd_params* params, co
     if (R < 0 || (R > 0 && (!X0 || !rng || !X || !f0 || !maxviol))) return fail(QCQP_ERR_INVALID, "qcqp_cd_improve: bad argument");
     if (R == 0) return QCQP_OK;
     const size_t n = pack->v.n;
-    DevBuf dX0, dX, dF, dM, dR, dS;
-    TRY(dX0.alloc(R * n * 8)); TRY(dX.alloc(R * n * 8)); TRY(dF.alloc(R * 8)); TRY(dM.alloc(R * 8));
-    TRY(dR.alloc(R * sizeof(qcqp_rng_state))); TRY(dS.alloc(R * sizeof(qcqp_cd_stats)));
-    QCQP_CUDA_TRY(cudaMemcpy(dX0.p, X0, R * n * 8, cudaMemcpyHostToDevice));
-    QCQP_CUDA_TRY(cudaMemcpy(dR.p, rng, R * sizeof(qcqp_rng_state), cudaMemcpyHostToDevice));
-    TRY(cd_launch(pack, params, dX0.as<double>(), R, dR.as<qcqp_rng_state>(), dX.as<double>(), dF.as<double>(), dM.as<double>(),
-                  dS.as<qcqp_cd_stats>(), 0));
+    TRY(ensure_io(pack, 2 * Arena::pad(R * n * 8) + 2 * Arena::pad(R * 8) + Arena::pad(R * sizeof(qcqp_rng_state)) +
+                            Arena::pad(R * sizeof(qcqp_cd_stats))));
+    Arena ar; ar.base = (char*)pack->io;
+    double* dX0 = ar.take<double>(R * n * 8); double* dX = ar.take<double>(R * n * 8);
+    double* dF = ar.take<double>(R * 8); double* dM = ar.take<double>(R * 8);
+    qcqp_rng_state* dR = ar.take<qcqp_rng_state>(R * sizeof(qcqp_rng_state));
+    qcqp_cd_stats* dS = ar.take<qcqp_cd_stats>(R * sizeof(qcqp_cd_stats));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(dX0, X0, R * n * 8, cudaMemcpyHostToDevice, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(dR, rng, R * sizeof(qcqp_rng_state), cudaMemcpyHostToDevice, 0));
+    TRY(cd_launch(pack, params, dX0, R, dR, dX, dF, dM, dS, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, R * n * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF, R * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, R * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(rng, dR, R * sizeof(qcqp_rng_state), cudaMemcpyDeviceToHost, 0));
+    if (stats) QCQP_CUDA_TRY(cudaMemcpyAsync(stats, dS, R * sizeof(qcqp_cd_stats), cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaStreamSynchronize(0));
-    QCQP_CUDA_TRY(cudaMemcpy(X, dX.p, R * n * 8, cudaMemcpyDeviceToHost));
-    QCQP_CUDA_TRY(cudaMemcpy(f0, dF.p, R * 8, cudaMemcpyDeviceToHost));
-    QCQP_CUDA_TRY(cudaMemcpy(maxviol, dM.p, R * 8, cudaMemcpyDeviceToHost));
-    QCQP_CUDA_TRY(cudaMemcpy(rng, dR.p, R * sizeof(qcqp_rng_state), cudaMemcpyDeviceToHost));
-    if (stats) QCQP_CUDA_TRY(cudaMemcpy(stats, dS.p, R * sizeof(qcqp_cd_stats), cudaMemcpyDeviceToHost));
     return QCQP_OK;
 }
 
@@ -158,17 +170,19 @@ extern "C" int qcqp_sdr_sample_eval(qcqp_pack* pack, const double* mu, const dou
     if (S < 0 || (S > 0 && (!mu || !F || !X || !f0 || !maxviol))) return fail(QCQP_ERR_INVALID, "qcqp_sdr_sample_eval: bad argument");
     if (S == 0) return QCQP_OK;
     const size_t n = pack->v.n;
-    DevBuf dMu, dFm, dZ, dX, dF0, dM;
-    TRY(dMu.alloc(n * 8)); TRY(dFm.alloc(n * n * 8)); TRY(dX.alloc(S * n * 8)); TRY(dF0.alloc(S * 8)); TRY(dM.alloc(S * 8));
-    if (Z) { TRY(dZ.alloc(S * n * 8)); QCQP_CUDA_TRY(cudaMemcpy(dZ.p, Z, S * n * 8, cudaMemcpyHostToDevice)); }
-    QCQP_CUDA_TRY(cudaMemcpy(dMu.p, mu, n * 8, cudaMemcpyHostToDevice));
-    QCQP_CUDA_TRY(cudaMemcpy(dFm.p, F, n * n * 8, cudaMemcpyHostToDevice));
-    TRY(sdr_launch(pack, dMu.as<double>(), dFm.as<double>(), Z ? dZ.as<double>() : nullptr, seed, S, dX.as<double>(), dF0.as<double>(),
-                   dM.as<double>(), 0));
+    TRY(ensure_io(pack, Arena::pad(n * 8) + Arena::pad(n * n * 8) + 2 * Arena::pad(S * n * 8) + 2 * Arena::pad(S * 8)));
+    Arena ar; ar.base = (char*)pack->io;
+    double* dMu = ar.take<double>(n * 8); double* dFm = ar.take<double>(n * n * 8);
+    double* dZ = ar.take<double>(S * n * 8); double* dX = ar.take<double>(S * n * 8);
+    double* dF0 = ar.take<double>(S * 8); double* dM = ar.take<double>(S * 8);
+    if (Z) QCQP_CUDA_TRY(cudaMemcpyAsync(dZ, Z, S * n * 8, cudaMemcpyHostToDevice, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(dMu, mu, n * 8, cudaMemcpyHostToDevice, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(dFm, F, n * n * 8, cudaMemcpyHostToDevice, 0));
+    TRY(sdr_launch(pack, dMu, dFm, Z ? dZ : nullptr, seed, S, dX, dF0, dM, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, S * n * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF0, S * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, S * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaStreamSynchronize(0));
-    QCQP_CUDA_TRY(cudaMemcpy(X, dX.p, S * n * 8, cudaMemcpyDeviceToHost));
-    QCQP_CUDA_TRY(cudaMemcpy(f0, dF0.p, S * 8, cudaMemcpyDeviceToHost));
-    QCQP_CUDA_TRY(cudaMemcpy(maxviol, dM.p, S * 8, cudaMemcpyDeviceToHost));
     return QCQP_OK;
 }
 

@@ -84,6 +84,9 @@ struct qcqp_pack {
     // workspace, grown on demand
     void* ws;
     size_t ws_bytes;
+    // device staging arena of the host-buffer entry points (grow-only, so steady-state calls do not cudaMalloc)
+    void* io;
+    size_t io_bytes;
     bool has_eig;
     int objective_dense;
 };
@@ -91,6 +94,7 @@ struct qcqp_pack {
 namespace qcqp {
 
 int ensure_workspace(qcqp_pack* p, size_t bytes);
+int ensure_io(qcqp_pack* p, size_t bytes);
 int num_sms(int device);
 int max_smem_optin(int device);
 

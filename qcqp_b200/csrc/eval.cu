@@ -57,7 +57,7 @@ int eval_launch(qcqp_pack* p, const double* dX, int R, double* df0, double* dmv,
 
 // ---------------------------------------------------------------------------------------------------------
 // best pick: lexicographic min on (int(maxviol / tol), f0); among exact ties the LATER index wins, which is what
-// folding `best = better(x_r, best)` over r = 0..R-1 does (better returns its second argument on a tie).
+// folding `best = better(best, x_r)` over r = 0..R-1 does (better returns its second argument on a tie).
 // Single CTA: R is a restart count (thousands), the whole reduction is a few microseconds.
 // ---------------------------------------------------------------------------------------------------------
 struct BestKey { long long bucket; double f; int idx; };

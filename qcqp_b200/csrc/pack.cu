@@ -44,6 +44,19 @@ int ensure_workspace(qcqp_pack* p, size_t bytes)
     return QCQP_OK;
 }
 
+int ensure_io(qcqp_pack* p, size_t bytes)
+{
+    if (bytes <= p->io_bytes) return QCQP_OK;
+    if (p->io) cudaFree(p->io);
+    p->io = nullptr;
+    p->io_bytes = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&p->io, want);
+    if (e != cudaSuccess) return fail(QCQP_ERR_NOMEM, std::string("staging cudaMalloc: ") + cudaGetErrorString(e));
+    p->io_bytes = want;
+    return QCQP_OK;
+}
+
 template <class T>
 static int upload(qcqp_pack* p, const std::vector<T>& h, const T** dptr)
 {
@@ -80,6 +93,7 @@ extern "C" void qcqp_pack_destroy(qcqp_pack* p)
     if (!p) return;
     for (void* d : p->allocs) cudaFree(d);
     if (p->ws) cudaFree(p->ws);
+    if (p->io) cudaFree(p->io);
     delete p;
 }
 
@@ -238,7 +252,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     qcqp_pack* p = new qcqp_pack();
     std::memset(&p->v, 0, sizeof(p->v));
     std::memset(&p->info, 0, sizeof(p->info));
-    p->ws = nullptr; p->ws_bytes = 0; p->has_eig = false;
+    p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->has_eig = false;
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;
     PackView& v = p->v;

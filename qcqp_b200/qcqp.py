@@ -1,0 +1,210 @@
+"""The CVXPY-facing Suggest-and-Improve facade: same class, methods and return values as the reference's QCQP
+(qcqp/qcqp.py:367-432), with the hot path running on the B200 engine.
+
+    qcqp = QCQP(prob)                 # a QCQPForm / list of (P, q, r, relop) / (if cvxpy is importable) a cvxpy Problem
+    f, v = qcqp.suggest(SDR)          # (objective, max violation) of the suggested point
+    f, v = qcqp.improve(COORD_DESCENT)
+
+Extensions (all optional): `samples=` / `restarts=` run many draws / restarts as one batch on the GPU and keep the best
+in QCQPForm.better order; `seed=` gives restart r the MT19937 stream of np.random.seed(seed + r).  With a single point
+and no seed the process-global np.random stream is consumed exactly as the reference consumes it.
+"""
+import logging
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import settings as s
+from . import engine
+from .forms import QCQPForm, QuadraticFunction
+
+log = logging.getLogger("qcqp_b200")   # the reference opens ./qcqp.log at import time (qcqp.py:39); this package does not
+
+
+def _form_from_cvxpy(prob):
+    """get_qcqp_form (utilities.py:318-347) for a cvxpy 0.4 Problem.  Only reachable when cvxpy 0.4 is installed."""
+    try:
+        from cvxpy.utilities import QuadCoeffExtractor
+    except Exception:
+        raise Exception("a cvxpy problem needs cvxpy 0.4 (QuadCoeffExtractor); pass a QCQPForm or a list of (P, q, r, relop) instead")
+    if not prob.objective.args[0].is_quadratic():
+        raise Exception("Objective is not quadratic.")
+    if not all([constr._expr.is_quadratic() for constr in prob.constraints]):
+        raise Exception("Not all constraints are quadratic.")
+    id_map, N = {}, 0
+    for x in prob.variables():
+        id_map[x.id] = N
+        N += x.size[0] * x.size[1]
+    extractor = QuadCoeffExtractor(id_map, N)
+    P0, q0, r0 = extractor.get_coeffs(prob.objective.args[0])
+    P0, q0, r0 = (P0[0] + P0[0].T) / 2., q0.T.tocsc(), r0[0]
+    maximize = prob.objective.NAME == "maximize"
+    if maximize:
+        P0, q0, r0 = -P0, -q0, -r0
+    fs = []
+    for constr in prob.constraints:
+        sz = constr._expr.size[0] * constr._expr.size[1]
+        Pc, qc, rc = extractor.get_coeffs(constr._expr)
+        for i in range(sz):
+            fs.append(QuadraticFunction((Pc[i] + Pc[i].T) / 2., qc[i, :].T.tocsc(), rc[i], constr.OP_NAME))
+    return QCQPForm(QuadraticFunction(P0, q0, r0), fs), maximize
+
+
+class QCQP:
+    def __init__(self, prob, maximize=False):
+        self.prob = prob
+        self._cvx_vars = None
+        if isinstance(prob, QCQPForm):
+            self.qcqp_form = prob
+        elif isinstance(prob, (list, tuple)):
+            self.qcqp_form = QCQPForm.from_tuples(list(prob))
+        else:
+            self.qcqp_form, maximize = _form_from_cvxpy(prob)
+            self._cvx_vars = prob.variables()
+        self.n = self.qcqp_form.n
+        self.maximize_flag = bool(maximize)
+        self.spectral_sol = None
+        self.spectral_bound = None
+        self.sdr_sol = None
+        self.sdr_bound = None
+        self.mu = None
+        self.Sigma = None
+        self._F = None
+        self.x = None          # current point (the reference keeps it in the cvxpy variables)
+        self.X = None          # current batch [R][n]
+        self._pack = engine.Pack(self.qcqp_form.forms())
+
+    # ---- helpers -----------------------------------------------------------------------------------------
+    def _sign(self, f):
+        return -f if self.maximize_flag else f
+
+    def _assign(self, X, f0, maxviol):
+        """Keeps the batch, selects the best point (QCQPForm.better order) and writes it back (assign_vars,
+        utilities.py:298-308, column-major per variable)."""
+        self.X = np.array(X, dtype=np.float64).reshape(-1, self.n)
+        self.batch_f0 = np.asarray([self._sign(v) for v in f0])
+        self.batch_maxviol = np.array(maxviol, dtype=np.float64)
+        b = engine.best(f0, maxviol) if len(f0) > 1 else 0
+        self.best_index = b
+        self.x = self.X[b].copy()
+        if self._cvx_vars is not None:
+            ind = 0
+            for v in self._cvx_vars:
+                size = v.size[0] * v.size[1]
+                v.value = np.reshape(self.x[ind:ind + size], v.size, order='F')
+                ind += size
+        return (self._sign(float(f0[b])), float(maxviol[b]))
+
+    def set_sdr_solution(self, X, bound=None):
+        """Supplies the relaxed solution X* (n+1 x n+1) of solve_sdr (qcqp.py:72-97) computed elsewhere."""
+        X = np.asarray(X, dtype=np.float64)
+        if X.shape != (self.n + 1, self.n + 1):
+            raise Exception("X* must be (n+1) x (n+1)")
+        self.sdr_sol = X
+        self.sdr_bound = None if bound is None else (-bound if self.maximize_flag else bound)
+        self.mu = None
+
+    # ---- suggest (qcqp.py:378-401) -----------------------------------------------------------------------
+    def suggest(self, method=s.RANDOM, eps=1e-8, *args, **kwargs):
+        if method not in s.suggest_methods:
+            raise Exception("Unknown suggest method: %s\n", method)
+        S = int(kwargs.pop("samples", 1))
+        if method == s.RANDOM:
+            X = np.stack([np.random.randn(self.n) for _ in range(S)])
+            f0, mv = self._pack.eval(X)
+            return self._assign(X, f0, mv)
+        if method == s.SPECTRAL:
+            if self.spectral_sol is None:
+                raise Exception("The spectral relaxation needs an SDP solve (solve_spectral, qcqp.py:41-70), which stays on the "
+                                "host and is out of scope of this engine; set qcqp.spectral_sol / spectral_bound yourself.")
+            X = np.asarray(self.spectral_sol, dtype=np.float64).reshape(1, self.n)
+            f0, mv = self._pack.eval(X)
+            return self._assign(X, f0, mv)
+        # SDR
+        if self.sdr_sol is None:
+            if "sdr_solution" in kwargs:
+                self.set_sdr_solution(kwargs.pop("sdr_solution"), kwargs.pop("sdr_bound", None))
+            else:
+                raise Exception("The SDP relaxation (solve_sdr, qcqp.py:72-97) stays on the host and no SDP solver is bundled: "
+                                "call qcqp.set_sdr_solution(X) or pass sdr_solution=X.")
+        if self.mu is None:
+            self.mu, self.Sigma, self._F = engine.sdr_factor(self.sdr_sol, eps=eps, corrected=bool(kwargs.pop("corrected", False)))
+        device_rng = kwargs.pop("device_rng", False)
+        if device_rng:
+            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=None, S=S, seed=int(kwargs.pop("seed", 0)))
+        else:
+            # np.random.multivariate_normal draws standard_normal(n) per sample from the global stream (SURVEY a-7)
+            Z = np.stack([np.random.standard_normal(self.n) for _ in range(S)])
+            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=Z)
+        return self._assign(X, f0, mv)
+
+    # ---- improve (qcqp.py:403-432) -----------------------------------------------------------------------
+    def _improve(self, method, *args, **kwargs):
+        X0 = self.X
+        R = X0.shape[0]
+        if method == s.COORD_DESCENT:
+            seed = kwargs.pop("seed", None)
+            kw = dict(num_iters=kwargs.get('num_iters', 1000), viol_tol=kwargs.get('viol_tol', 1e-2), tol=kwargs.get('tol', 1e-4),
+                      phase1=kwargs.get('phase1', True), strict=kwargs.get('strict', False))
+            if seed is None and R == 1:
+                rng = engine.rng_states(states=[np.random.get_state()])   # the reference's process-global stream
+            else:
+                base = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+                rng = engine.rng_states(seeds=[(base + r) % (2 ** 32) for r in range(R)])
+            X, f0, mv, stats = self._pack.cd_improve(X0, rng, **kw)
+            for r in range(R):
+                if stats[r].status == 1:
+                    raise ValueError("max() arg is an empty sequence")          # qcqp.py:117
+                if stats[r].status == 2:
+                    raise OverflowError("Range exceeds valid bounds")           # utilities.py:267
+            if seed is None and R == 1:
+                np.random.set_state(engine.rng_state_tuple(rng[0]))
+            self.cd_stats = stats
+            return self._assign(X, f0, mv)
+        if method == s.ADMM:
+            num_iters = kwargs.get('num_iters', 1000)
+            viol_lim = kwargs.get('viol_lim', 1e4)
+            tol = kwargs.get('tol', 1e-2)
+            rho = kwargs.get('rho', None)
+            phase1 = kwargs.get('phase1', True)
+            P0 = np.asarray(self.qcqp_form.f0.P.todense())
+            lmb_min = float(np.min(np.linalg.eigh(P0)[0]))
+            m = self.qcqp_form.m
+            rhos = None if rho is None else np.atleast_1d(np.asarray(rho, dtype=np.float64))
+            if rhos is not None:
+                for rv in rhos:
+                    if lmb_min + m * rv < 0:
+                        log.error("rho parameter is too small, z-update not convex.")
+                        raise Exception("rho parameter is too small, need at least %.3f." % rv)   # sic, qcqp.py:268
+            else:
+                rv = 2. * (1. - lmb_min) / m if lmb_min < 0 else 1. / m
+                rv *= 50.
+                log.warning("Automatically setting rho to %.3f", rv)
+                rhos = np.array([rv])
+            X, f0, mv, stats = self._pack.admm_improve(X0, rhos, num_iters=num_iters, viol_lim=viol_lim, tol=tol, phase1=phase1)
+            self.admm_stats = stats
+            self.admm_rhos = rhos
+            return self._assign(X.reshape(-1, self.n), f0.ravel(), mv.ravel())
+        if method == s.DCCP:
+            raise Exception("DCCP package is not installed.")       # qcqp.py:289-292; third-party wrapper, out of scope
+        if method == s.IPOPT:
+            raise Exception("PyIpopt package is not installed.")    # qcqp.py:326-329; third-party wrapper, out of scope
+
+    def improve(self, method, *args, **kwargs):
+        if not isinstance(method, list):
+            methods = [method]
+        else:
+            methods = method
+        if not all([mm in s.improve_methods for mm in methods]):
+            raise Exception("Unknown improve method(s): ", methods)
+        if self.X is None:
+            # the reference means to start from suggest() when no point exists (qcqp.py:427; its test on Variable objects
+            # never fires -- SURVEY H7 -- the intent is kept here)
+            self.suggest(samples=int(kwargs.pop("restarts", 1)))
+        restarts = kwargs.pop("restarts", None)
+        if restarts is not None and self.X.shape[0] != int(restarts):
+            raise Exception("restarts=%d but the current batch holds %d points; call suggest(samples=%d) first"
+                            % (int(restarts), self.X.shape[0], int(restarts)))
+        for mm in methods:
+            f, v = self._improve(mm, *args, **kwargs)
+        return (f, v)

@@ -1,0 +1,148 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/qcqp_b200.h declares, fails
+loudly without a device, the host logic (form flattening, sharding, best-pick order) is right, and the N>1 path works
+over gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from qcqp_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "qcqp_b200.h")).read()
+    declared = set(re.findall(r"\b(qcqp_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "libqcqp_b200.so does not export %s" % name
+    assert set(_lib.EXPORTS) == declared, (set(_lib.EXPORTS) ^ declared)
+    assert b"sm_100a" in _lib.load().qcqp_version()
+
+
+def test_struct_layouts_match_header():
+    from qcqp_b200 import _lib
+    assert C.sizeof(_lib.RngState) == 624 * 4 + 16
+    assert C.sizeof(_lib.CdStats) == 56 and C.sizeof(_lib.CdParams) == 40 and C.sizeof(_lib.AdmmStats) == 24
+
+
+def test_no_device_fails_loudly():
+    """No CPU fallback: without a GPU every entry point reports QCQP_ERR_NO_DEVICE instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from qcqp_b200 import engine, problems as pb
+    forms, _ = pb.boolean_least_squares(6, 9)
+    with pytest.raises(Exception, match="no CUDA device"):
+        engine.Pack(forms)
+    with pytest.raises(Exception, match="no CUDA device"):
+        engine.best([1.0], [0.0])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "qcqp_b200")
+    for base, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "qcqp_oracle" not in txt and "libqcqp_oracle" not in txt, f
+
+
+def test_flatten_forms_layout():
+    from qcqp_b200 import engine, problems as pb
+    forms, _ = pb.circle_packing(3)
+    f = engine.flatten_forms(forms)
+    assert f["n"] == 7 and f["m"] == len(forms) - 1
+    assert f["p_ptr"][0] == 0 and f["p_ptr"][-1] == len(f["p_val"]) and np.all(np.diff(f["p_ptr"]) >= 0)
+    for j in range(f["m"] + 1):
+        a, b = f["p_ptr"][j], f["p_ptr"][j + 1]
+        key = f["p_row"][a:b].astype(np.int64) * f["n"] + f["p_col"][a:b]
+        assert np.all(np.diff(key) > 0)
+        qa, qb = f["q_ptr"][j], f["q_ptr"][j + 1]
+        dense_q = np.zeros(f["n"]); dense_q[f["q_idx"][qa:qb]] = f["q_val"][qa:qb]
+        assert np.array_equal(dense_q, np.asarray(forms[j][1], dtype=float))
+    assert not np.any(f["p_val"] == 0.0)
+
+
+def test_rng_state_roundtrip():
+    from qcqp_b200 import engine
+    rs = np.random.RandomState(5); rs.standard_normal(3)
+    arr = engine.rng_states(states=[rs.get_state()])
+    back = engine.rng_state_tuple(arr[0])
+    rs2 = np.random.RandomState(0); rs2.set_state(back)
+    assert rs2.uniform() == rs.uniform()
+
+
+def test_shard_ranges_cover_everything():
+    from qcqp_b200.dist import shard_range
+    for total in (0, 1, 7, 256, 1024, 4097):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_local_best_is_the_better_fold():
+    """local_best == folding `best = better(best, x_r)` over r with QCQPForm.better (utilities.py:135-146), which returns
+    its SECOND argument on an exact tie -- hence "later index wins"."""
+    from qcqp_b200.dist import local_best
+
+    def better_returns_first(mv1, f1, mv2, f2, tol=1e-4):
+        v1, v2 = int(mv1 / tol), int(mv2 / tol)
+        if v1 < v2: return True
+        if v2 < v1: return False
+        return f1 < f2
+
+    rs = np.random.RandomState(3)
+    for t in range(200):
+        R = int(rs.randint(1, 40))
+        f0 = np.round(rs.randn(R), 1)
+        mv = np.abs(rs.randn(R)) * 10.0 ** rs.randint(-6, 0, size=R)
+        best = 0
+        for r in range(1, R):
+            if not better_returns_first(mv[best], f0[best], mv[r], f0[r]):
+                best = r
+        assert local_best(f0, mv)[2] == best
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from qcqp_b200.dist import shard_range, local_best, global_best, broadcast_point
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+rs = np.random.RandomState(0)
+R, n = 37, 5
+f0 = np.round(rs.randn(R), 1); mv = np.abs(rs.randn(R)) * 1e-3; X = rs.randn(R, n)
+lo, hi = shard_range(R, rank, 2)
+b, f, i = local_best(f0[lo:hi], mv[lo:hi])
+gb, gf, gi = global_best(b, f, lo + i if i >= 0 else -1)
+want = local_best(f0, mv)
+assert (gb, gf, gi) == want, ((gb, gf, gi), want)
+owner = 0 if gi < shard_range(R, 0, 2)[1] else 1
+x = broadcast_point(X[gi] if rank == owner else np.zeros(n), owner, n)
+assert np.array_equal(x, X[gi])
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_gloo_world_size_2_best_pick(tmp_path):
+    """The N>1 path (sharded restarts + best-pick reduction + winner broadcast) on two CPU ranks over gloo."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + (os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "OK %d" % r in o, o

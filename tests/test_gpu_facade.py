@@ -1,0 +1,84 @@
+"""The Suggest-and-Improve facade on the GPU: the reference's example flows (examples/*.py), parity of the single-point
+drop-in mode with the process-global np.random stream, batch mode, error behaviour."""
+import numpy as np
+import pytest
+
+from helpers import rel_close
+
+pytestmark = pytest.mark.gpu
+
+
+def test_boolean_least_squares_example_flow():
+    """examples/boolean_least_squares.py:6-38 with a supplied X* (the SDP solve stays on the host, out of scope)."""
+    from oracle import oracle as orc
+    import qcqp_b200 as Q
+    from qcqp_b200 import problems as pb
+    forms, info = pb.boolean_least_squares(10, 15, seed=1)
+    qc = Q.QCQP(forms)
+    qc.set_sdr_solution(pb.synthetic_sdr_solution(10, rank=3, seed=5))
+    P = orc.Problem(forms)
+    # reference-side replay of the same calls on the oracle, sharing the global stream semantics
+    np.random.seed(3)
+    f_s, v_s = qc.suggest(Q.SDR)
+    x_s = qc.x.copy()
+    f_cd, v_cd = qc.improve(Q.COORD_DESCENT)
+    state_after = np.random.get_state()
+    np.random.seed(3)
+    mu, Sigma, F = orc.sdr_factor(pb.synthetic_sdr_solution(10, rank=3, seed=5))
+    st = orc.RngState.from_numpy(np.random.mtrand._rand)
+    xo, _z = orc.sdr_sample(mu, F, st)
+    assert rel_close(x_s, xo, rtol=1e-10, atol=1e-12)
+    assert rel_close(f_s, P.eval(0, xo), rtol=1e-10) and rel_close(v_s, P.max_violation(xo), rtol=1e-10)
+    xc, so = P.improve_cd(xo, st, fast=True)
+    assert rel_close(f_cd, P.eval(0, xc), rtol=1e-6) and rel_close(v_cd, P.max_violation(xc), rtol=1e-6, atol=1e-10)
+    assert state_after[2] == st.pos and np.array_equal(state_after[1], np.frombuffer(st.key, dtype=np.uint32))
+    # chained improves, as the example does
+    f2, v2 = qc.improve([Q.COORD_DESCENT, Q.ADMM], phase1=False, rho=2.0, num_iters=50)
+    assert v2 < 1e-2 + 1e-9 or f2 <= f_cd + 1e-6
+
+
+def test_maxcut_maximize_and_batch():
+    import qcqp_b200 as Q
+    from qcqp_b200 import problems as pb
+    forms, info = pb.maxcut(25, 0.2, seed=1)
+    qc = Q.QCQP(forms, maximize=True)
+    qc.set_sdr_solution(pb.synthetic_sdr_solution(25, rank=4, seed=2))
+    np.random.seed(11)
+    f, v = qc.suggest(Q.SDR, samples=64)
+    assert qc.X.shape == (64, 25)
+    fb, vb = qc.improve(Q.COORD_DESCENT, seed=100, num_iters=50)
+    assert vb < 1e-2 and fb > 0           # a cut value, sign flipped back (qcqp.py:400,416)
+    assert fb == qc.batch_f0[qc.best_index] and fb >= np.max(qc.batch_f0[qc.batch_maxviol < 1e-4 * (int(vb / 1e-4) + 1)]) - 1e-12
+    W = info["W"]
+    cut = 0.25 * (W.sum() - qc.x.dot(W).dot(qc.x))
+    assert rel_close(cut, fb, rtol=1e-9)
+
+
+def test_beamforming_admm_flow():
+    import qcqp_b200 as Q
+    from qcqp_b200 import problems as pb
+    forms, _ = pb.beamforming(n=20, m=5, l=2, seed=1)
+    qc = Q.QCQP(forms)
+    np.random.seed(4)
+    qc.suggest(Q.RANDOM)
+    f, v = qc.improve(Q.ADMM, rho=np.sqrt(7))
+    assert v <= 1e-2 and 5 < f < 40
+    with pytest.raises(Exception, match="rho parameter is too small"):
+        Q.QCQP([(forms[0][0] * -1.0, forms[0][1], 0.0, None)] + forms[1:]).improve(Q.ADMM, rho=1e-3)
+
+
+def test_facade_errors():
+    import qcqp_b200 as Q
+    from qcqp_b200 import problems as pb
+    forms, _ = pb.boolean_least_squares(6, 9, seed=1)
+    qc = Q.QCQP(forms)
+    with pytest.raises(Exception, match="Unknown suggest method"):
+        qc.suggest("nope")
+    with pytest.raises(Exception, match="Unknown improve method"):
+        qc.improve("nope")
+    with pytest.raises(Exception, match="DCCP package is not installed"):
+        qc.suggest(Q.RANDOM); qc.improve(Q.DCCP)
+    with pytest.raises(Exception, match="PyIpopt package is not installed"):
+        qc.improve(Q.IPOPT)
+    with pytest.raises(Exception, match="SDP"):
+        Q.QCQP(forms).suggest(Q.SDR)

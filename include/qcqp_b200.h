@@ -93,8 +93,11 @@ typedef struct {
     double viol_tol;        /* 1e-2 */
     double tol;             /* 1e-4 */
     int32_t phase1;         /* 1 */
-    int32_t strict;         /* 1: row dots summed sequentially in column order with separately rounded
-                                  multiply/add, like SciPy's csr_matvec (bit-exact t1; slow).  0: warp-parallel fma. */
+    int32_t strict;         /* 0 (default): fast -- dense row dots come from a cached g = P x kept current by an axpy on every
+                                  move (the rows still stream through the TMA ring; the dot leaves the critical path).
+                               1: strict -- every row dot summed sequentially in column order with separately rounded
+                                  multiply/add, like SciPy's csr_matvec (bit-exact t1; slow).
+                               2: fresh -- warp-parallel fma dot of the staged row at every step. */
     int32_t refresh_every;  /* recompute the cached f_j(x) from scratch every this many phase-2 sweeps; 0 = 64 */
 } qcqp_cd_params;
 

@@ -26,17 +26,20 @@ struct CdLayout {
     int S;            // ring stages (0: no dense forms)
     int sc_cap;       // coefficient scratch entries in smem (0: global scratch)
     int fval_smem;    // cached f_j in smem?
+    int grad;         // cached dense row dots g_d = P_d x in smem (gradient mode)
     int evN;          // event capacity (power of two)
     // byte offsets inside the dynamic smem block
     unsigned off_bar, off_ring, off_warp0, warp_stride;
-    unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_evk, o_evd, o_clo, o_chi, o_dd, o_misc;
+    unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_evk, o_evd, o_clo, o_chi, o_dd, o_misc, o_g;
     unsigned total;
 };
+
+enum { MODE_GRAD = 0, MODE_STRICT = 1, MODE_FRESH = 2 };
 
 struct CdK {
     int num_iters;
     double viol_tol, tol;
-    int phase1, strict, refresh_every;
+    int phase1, mode, refresh_every;
 };
 
 struct WarpMem {
@@ -47,6 +50,7 @@ struct WarpMem {
     double* evk; int* evd;
     double* clo; double* chi;
     double* dd;       // dots of the dense rows of this step, by dense slot
+    double* g;        // gradient mode: g[d][npad] = P_d x for every dense slot
     int* misc;        // [0] event counter
 };
 
@@ -282,12 +286,127 @@ __device__ __forceinline__ int solve_small(const WarpMem& w, bool active, double
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cached f_j(x) from scratch; returns max constraint violation (warp-uniform)
+// Phase-1 bisection for a coordinate with ONE counted constraint (every Boolean-type problem): the reference probes
+// s = (ss+es)/2 one level at a time (qcqp.py:122-131).  Here 31 lanes evaluate the 31 nodes of the next five levels of
+// that decision tree at once -- each lane replays the same (ss+es)/2 arithmetic along its own path, so the s values are
+// the reference's bit for bit -- and then the warp walks the actual path, lane 0 drawing the random numbers of the
+// feasible probes in the reference's order.  Returns false when the reference would have raised (err set).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double refresh_fvals(const PackView& P, const WarpMem& w, int j0, bool strict, int lane)
+__device__ __forceinline__ bool spec_bisect(double p, double q, double r, int rel, double tol, double& ss, double& es, double& new_xi,
+                                            double& new_viol, MtRng& rng, int lane, int* err)
+{
+    *err = 0;
+    while (es - ss > tol) {
+        // ---- my node: lane L <-> node v = L + 1 (root = 1; child 2v = infeasible branch, 2v+1 = feasible branch) ----
+        const int v = lane + 1;
+        const int depth = 31 - __clz(v);
+        double lss = ss, les = es;
+        bool nodeok = (lane < 31);
+        for (int i = depth - 1; i >= 0 && nodeok; i--) {
+            if (!(les - lss > tol)) { nodeok = false; break; }
+            const double sm = (lss + les) / 2;
+            if ((v >> i) & 1) les = sm; else lss = sm;
+        }
+        nodeok = nodeok && (les - lss > tol);
+        const double sv = (lss + les) / 2;
+        int nC = 0;
+        double cl[4], ch[4];
+        cl[0] = cl[1] = ch[0] = ch[1] = 0.0;
+        if (nodeok) {
+            Fold f;
+            f.init();
+            f.mcnt = 1;
+            Ival I[2];
+            const int c = feasible_intervals(p, q, r, rel, sv, I);
+            if (c == 1) f.add_single(I[0].lo, I[0].hi);
+            if (c > 0) nC = sweep_small8(f, c == 2, I[0], I[1], cl, ch);
+        }
+        const unsigned okmask = __ballot_sync(FULL, nodeok);
+        const unsigned feas = __ballot_sync(FULL, nodeok && nC > 0);
+        // ---- walk the path actually taken ----
+        int node = 1;
+#pragma unroll 1
+        for (int lvl = 0; lvl < 5; lvl++) {
+            const int src = node - 1;
+            if (!((okmask >> src) & 1u)) break;          // es - ss <= tol here: the while loop of the reference ends
+            const double s = __shfl_sync(FULL, sv, src);
+            if ((feas >> src) & 1u) {
+                const int k = __shfl_sync(FULL, nC, src);
+                const double a0 = __shfl_sync(FULL, cl[0], src), b0 = __shfl_sync(FULL, ch[0], src);
+                const double a1 = __shfl_sync(FULL, cl[1], src), b1 = __shfl_sync(FULL, ch[1], src);
+                double xv = 0.0;
+                int e = 0;
+                if (lane == 0) {
+                    // onevar_qcqp with the zero objective: np.random.uniform(*C[np.random.choice(len(C))])  (utilities.py:266-267)
+                    const int idx = rng.choice(k);
+                    const double lo = idx ? a1 : a0, hi = idx ? b1 : b0;
+                    if (is_inf(lo) || is_inf(hi)) e = QCQP_RUN_UNBOUNDED_UNIFORM;
+                    else xv = rng.uniform(lo, hi);
+                }
+                e = bcast_i(e, 0);
+                if (e) { *err = e; return false; }
+                new_xi = bcast(xv, 0);
+                new_viol = s;
+                es = s;
+                node = 2 * node + 1;
+            } else {
+                ss = s;
+                node = 2 * node;
+            }
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gradient mode: g_d = P_d x for dense slot d from scratch (lanes own column pairs, rows stream coalesced from L2), and
+// f_d(x) = x.g_d + q_d.x + r_d from it.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void refresh_dense_slot(const PackView& P, const WarpMem& w, int d, int npad, int lane)
+{
+    const int n = P.n, ld = P.ld, j = P.dense_form[d];
+    const double* M = P.dense_P + (size_t)d * n * ld;
+    double* g = w.g + (size_t)d * npad;
+    const int n2 = (n + 1) >> 1;                  // ld is even and the pad column is zero, so pairs never run off a row
+    for (int c0 = 0; c0 < n2; c0 += 128) {
+        double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+        const int c = c0 + lane;
+        const bool v0 = c < n2, v1 = c + 32 < n2, v2 = c + 64 < n2, v3 = c + 96 < n2;
+        for (int r = 0; r < n; r++) {
+            const double xr = w.x[r];
+            const double2* row = reinterpret_cast<const double2*>(M + (size_t)r * ld);
+            if (v0) { const double2 t = row[c]; a0.x = fma(t.x, xr, a0.x); a0.y = fma(t.y, xr, a0.y); }
+            if (v1) { const double2 t = row[c + 32]; a1.x = fma(t.x, xr, a1.x); a1.y = fma(t.y, xr, a1.y); }
+            if (v2) { const double2 t = row[c + 64]; a2.x = fma(t.x, xr, a2.x); a2.y = fma(t.y, xr, a2.y); }
+            if (v3) { const double2 t = row[c + 96]; a3.x = fma(t.x, xr, a3.x); a3.y = fma(t.y, xr, a3.y); }
+        }
+        double2* g2 = reinterpret_cast<double2*>(g);
+        if (v0) g2[c] = a0;
+        if (v1) g2[c + 32] = a1;
+        if (v2) g2[c + 64] = a2;
+        if (v3) g2[c + 96] = a3;
+    }
+    __syncwarp();
+    double acc = 0.0;
+    for (int c = lane; c < n; c += 32) acc = fma(w.x[c], g[c], acc);
+    for (long long e = P.q_ptr[j] + lane; e < P.q_ptr[j + 1]; e += 32) acc = fma(P.q_val[e], w.x[P.q_idx[e]], acc);
+    acc = warp_sum(acc) + P.r[j];
+    if (lane == 0) w.fval[j] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cached f_j(x) (and, in gradient mode, g_d) from scratch for forms j >= j0; returns max constraint violation
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double refresh_fvals(const PackView& P, const WarpMem& w, int j0, int mode, int npad, int lane)
 {
     double* fv = w.fval;
-    eval_forms(P, w.x, j0, P.m, strict, lane, [&](int j, double v) { fv[j] = v; });
+    if (mode == MODE_GRAD) {
+        eval_forms(P, w.x, j0, P.m, false, lane, [&](int j, double v) { fv[j] = v; }, /*skip_dense=*/true);
+        for (int d = 0; d < P.n_dense; d++)
+            if (P.dense_form[d] >= j0) refresh_dense_slot(P, w, d, npad, lane);
+    } else {
+        eval_forms(P, w.x, j0, P.m, mode == MODE_STRICT, lane, [&](int j, double v) { fv[j] = v; }, false);
+    }
     __syncwarp();
     double mv = -QCQP_INF;
     for (int j = 1 + lane; j <= P.m; j += 32) {
@@ -327,6 +446,25 @@ __device__ __forceinline__ double sparse_dot_warp(const PackView& P, int rbeg, i
     return warp_sum(s);
 }
 
+// gradient mode, after x_k += delta: g_d += delta * (row k of P_d) for the maintained dense slots (P_d symmetric)
+__device__ __forceinline__ void grad_axpy(const WarpMem& w, const double* rows, int d0, int nd, int n, int ld, int npad, double delta,
+                                          int lane)
+{
+    __builtin_assume(__isShared(rows));
+    const int n2 = (n + 1) >> 1;
+    for (int d = d0; d < nd; d++) {
+        const double2* r2 = reinterpret_cast<const double2*>(rows + (size_t)d * ld);
+        double2* g2 = reinterpret_cast<double2*>(w.g + (size_t)d * npad);
+        for (int c = lane; c < n2; c += 32) {
+            const double2 rv = r2[c];
+            double2 gv = g2[c];
+            gv.x = fma(rv.x, delta, gv.x);
+            gv.y = fma(rv.y, delta, gv.y);
+            g2[c] = gv;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -339,6 +477,9 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
     const int n = P.n, m = P.m, nd = P.n_dense, ld = P.ld;
     const int W = lay.W, S = lay.S;
     const bool ring = (nd > 0);
+    const int mode = prm.mode;
+    const int npad = (n + 1) & ~1;
+    const bool obj_dense = ring && P.dense_form[0] == 0;
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
     uint64_t* bar_empty = bar_full + (S > 0 ? S : 1);
     double* ringbuf = reinterpret_cast<double*>(smem + lay.off_ring);
@@ -354,14 +495,20 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
     if (ring && warp == W) {
         unsigned slot = 0;
         for (;;) {
-            if (!__syncthreads_or(0)) break;   // pairs with the restart warps' vote at every sweep boundary
+            if (!__syncthreads_or(0)) break;   // pairs with the restart warps' votes at every sweep boundary
+            // phase 1 never reads the objective: its rows are streamed only while some restart of this CTA is in phase 2
+            const int d0 = (obj_dense && !__syncthreads_or(0)) ? 1 : 0;
             for (int k = 0; k < n; k++, slot++) {
                 int st = slot % S;
                 if (slot >= (unsigned)S) mbar_wait(&bar_empty[st], ((slot / S) + 1) & 1);
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(&bar_full[st], row_bytes * nd);
-                    for (int d = 0; d < nd; d++)
-                        bulk_g2s(ringbuf + ((size_t)st * nd + d) * ld, P.dense_P + ((size_t)d * n + k) * ld, row_bytes, &bar_full[st]);
+                    if (nd - d0 > 0) {
+                        mbar_arrive_expect_tx(&bar_full[st], row_bytes * (nd - d0));
+                        for (int d = d0; d < nd; d++)
+                            bulk_g2s(ringbuf + ((size_t)st * nd + d) * ld, P.dense_P + ((size_t)d * n + k) * ld, row_bytes, &bar_full[st]);
+                    } else {
+                        mbar_arrive(&bar_full[st]);
+                    }
                 }
                 __syncwarp();
             }
@@ -382,6 +529,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
     w.chi = reinterpret_cast<double*>(wb + lay.o_chi);
     w.dd = reinterpret_cast<double*>(wb + lay.o_dd);
     w.misc = reinterpret_cast<int*>(wb + lay.o_misc);
+    w.g = reinterpret_cast<double*>(wb + lay.o_g);
     const size_t rr = live ? (size_t)restart : 0;
     w.fval = lay.fval_smem ? reinterpret_cast<double*>(wb + lay.o_fval) : ws_fval + rr * (size_t)(m + 1);
     if (lay.sc_cap > 0) {
@@ -412,7 +560,8 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
     }
     __syncwarp();
 
-    const bool strict = prm.strict != 0;
+    const bool strict = (mode == MODE_STRICT);
+    const bool grad = (mode == MODE_GRAD) && ring;
     const double tol = prm.tol, viol_tol = prm.viol_tol;
     int t = 0;                    // sweeps done in the current phase
     long long update_counter = 0;
@@ -431,17 +580,18 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
         if (phase == PH_P1) {
             if (p1_over || t >= prm.num_iters || viol_last < viol_tol) {
                 // improve_coord_descent: if max(prob.violations(x)) < viol_tol: phase 2   (qcqp.py:189-190)
-                double mv = refresh_fvals(P, w, 0, strict, lane);
+                double mv = refresh_fvals(P, w, 0, mode, npad, lane);
                 if (m == 0) { st.status = QCQP_RUN_EMPTY_MAX; phase = PH_DONE; }
                 else if (mv < viol_tol) { phase = PH_P2; viol_p2 = mv; t = 0; update_counter = 0; st.ran_phase2 = 1; }
                 else phase = PH_DONE;
             } else if (t == 0) {
-                refresh_fvals(P, w, 1, strict, lane);
+                refresh_fvals(P, w, 1, mode, npad, lane);
             }
         }
         if (phase == PH_P2 && t >= prm.num_iters) phase = PH_DONE;
         if (ring) {
             if (!__syncthreads_or(phase != PH_DONE)) break;
+            if (obj_dense) __syncthreads_or(phase == PH_P2);   // tells the producer whether objective rows are needed
         } else if (phase == PH_DONE) break;
         if (phase == PH_P1) st.sweeps_p1++;
         if (phase == PH_P2) st.sweeps_p2++;
@@ -463,18 +613,25 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
             double xk = 0.0;
             if (work) {
                 xk = w.x[k];
-                __syncwarp();
-                if (lane == 0) w.x[k] = 0.0;
-                __syncwarp();
+                if (!grad) {
+                    __syncwarp();
+                    if (lane == 0) w.x[k] = 0.0;
+                    __syncwarp();
+                }
             }
-            // ---- dense rows of this coordinate: dot each against z ----
+            // ---- dense rows of this coordinate: (P_d z)_k for every dense slot d ----
+            const int sg = ring ? (int)(slot % S) : 0;
+            const double* rows = ringbuf + (size_t)sg * nd * ld;
+            const int dfirst = (phase == PH_P1 && obj_dense) ? 1 : 0;     // phase 1 never touches the objective
             if (ring) {
-                const int sg = slot % S;
                 mbar_wait(&bar_full[sg], (slot / S) & 1);
                 if (work) {
-                    const double* rows = ringbuf + (size_t)sg * nd * ld;
-                    if (!strict) {
-                        for (int d = (phase == PH_P1 && P.dense_form[0] == 0) ? 1 : 0; d < nd; d++) {
+                    if (grad) {
+                        // cached g_d = P_d x: (P_d z)_k = g_d[k] - P_d[k,k] x_k; the row itself is only needed if x_k moves
+                        for (int d = dfirst + lane; d < nd; d += 32)
+                            w.dd[d] = w.g[(size_t)d * npad + k] - rows[(size_t)d * ld + k] * xk;
+                    } else if (!strict) {
+                        for (int d = dfirst; d < nd; d++) {
                             double v = dense_row_dot_warp(rows + (size_t)d * ld, w.x, n, lane);
                             if (lane == 0) w.dd[d] = v;
                         }
@@ -483,7 +640,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_empty[sg]);
+                if (!grad || !work) { if (lane == 0) mbar_arrive(&bar_empty[sg]); }
             }
             if (!work) {
                 if (!ring) break;
@@ -535,7 +692,14 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                         const double viol = warp_max(nz ? violation_of(crel, onevar_eval(cp, cq, cr, xk)) : -QCQP_INF);
                         double new_viol = viol;
                         double ss = -tol, es = viol - viol_tol;
-                        while (es - ss > tol) {
+                        const unsigned nzmask = __ballot_sync(FULL, nz);
+                        if (__popc(nzmask) == 1) {
+                            const int src = __ffs(nzmask) - 1;
+                            int err;
+                            if (!spec_bisect(bcast(cp, src), bcast(cq, src), bcast(cr, src), bcast_i(crel, src), tol, ss, es, new_xi,
+                                             new_viol, rng, lane, &err)) { st.status = err; dead = true; }
+                        }
+                        while (!dead && es - ss > tol) {
                             const double s = (ss + es) / 2;
                             double xi;
                             int err;
@@ -568,6 +732,11 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                 // f_j(x) = t0 + b (t2 b + t1) for every incident form; x_k back in place (moved or not)
                 if (move && need) w.fval[form] = cr + new_xi * (cp * new_xi + cq);
                 if (lane == 0) w.x[k] = new_xi;
+                if (grad) {
+                    if (move) grad_axpy(w, rows, dfirst, nd, n, ld, npad, new_xi - xk, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_empty[sg]);
+                }
                 if (dead) phase = PH_DONE;
                 __syncwarp();
                 continue;
@@ -676,12 +845,17 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                 if (lane == 0 && phase != PH_P1 && obj_inc) w.fval[0] = r0 + b * (p0 * b + q0);
             }
             if (lane == 0) w.x[k] = new_xi;
+            if (grad) {
+                if (move) grad_axpy(w, rows, dfirst, nd, n, ld, npad, new_xi - xk, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[sg]);
+            }
             if (dead) phase = PH_DONE;
             __syncwarp();
         }
         // ---------------- end of sweep ----------------
         if (phase == PH_P1) {
-            double mv = refresh_fvals(P, w, 1, strict, lane);   // viol = max(prob.violations(x))  (qcqp.py:142)
+            double mv = refresh_fvals(P, w, 1, mode, npad, lane);   // viol = max(prob.violations(x))  (qcqp.py:142)
             viol_last = mv;
             t++;
             if (!skip && st.updates_p1 == upd_before && !(viol_last < viol_tol) && t < prm.num_iters) {
@@ -692,13 +866,13 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
             }
         } else if (phase == PH_P2) {
             t++;
-            if (prm.refresh_every > 0 && (t % prm.refresh_every) == 0) refresh_fvals(P, w, 0, strict, lane);
+            if (prm.refresh_every > 0 && (t % prm.refresh_every) == 0) refresh_fvals(P, w, 0, mode, npad, lane);
         }
     }
 
     // ---------------- results: x, (f0.eval(x), max(violations(x))) as QCQP._improve returns them (qcqp.py:415-417) -------
     if (live) {
-        double mv = refresh_fvals(P, w, 0, strict, lane);
+        double mv = refresh_fvals(P, w, 0, mode == MODE_GRAD ? MODE_FRESH : mode, npad, lane);   // final values: full evaluation
         for (int i = lane; i < n; i += 32) X[rr * n + i] = w.x[i];
         for (int i = lane; i < 624; i += 32) rngs[rr].key[i] = w.mt[i];
         if (lane == 0) {
@@ -715,7 +889,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
 // ---------------------------------------------------------------------------------------------------------
 static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
-static int plan_layout(const qcqp_pack* p, int R, CdLayout* L)
+static int plan_layout(const qcqp_pack* p, int R, bool want_grad, CdLayout* L)
 {
     const PackView& v = p->v;
     const int smem_max = max_smem_optin(p->device);
@@ -741,21 +915,31 @@ static int plan_layout(const qcqp_pack* p, int R, CdLayout* L)
     l.o_chi = o; o += align_up((unsigned)(evN / 2 + 2) * 8, 16);
     l.o_dd = o; o += align_up((unsigned)(v.n_dense > 0 ? v.n_dense : 1) * 8, 16);
     l.o_misc = o; o += 16;
-    l.warp_stride = align_up(o, 128);
+    l.o_g = o;
+    const unsigned g_bytes = (unsigned)v.n_dense * (unsigned)((v.n + 1) & ~1) * 8;
+    const unsigned stride_nograd = align_up(o, 128);
+    l.grad = 0;
+    if (want_grad && v.n_dense > 0) {
+        // the cached row dots must leave room for at least one restart next to a 2-stage ring
+        if ((size_t)align_up(o + g_bytes, 128) + 256 + 2 * (size_t)v.n_dense * v.ld * 8 <= (size_t)smem_max) { l.grad = 1; o += g_bytes; }
+    }
+    l.warp_stride = l.grad ? align_up(o, 128) : stride_nograd;
 
     const unsigned stage_bytes = (unsigned)v.n_dense * v.ld * 8;
     int W, S = 0;
     if (v.n_dense > 0) {
-        S = 4;
-        while (S > 2 && (size_t)S * stage_bytes > (size_t)smem_max / 3) S--;
-        unsigned fixed = 256 + align_up(S * stage_bytes, 128);
-        if (fixed + l.warp_stride > (unsigned)smem_max)
-            return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: one restart plus the dense-row ring exceeds shared memory");
-        int wmax = (int)((smem_max - fixed) / l.warp_stride);
-        if (wmax > 7) wmax = 7;   // 7 restart warps + the producer = 256 threads, 255 registers each
         W = (R + sms - 1) / sms;          // spread the restarts over all SMs first, then share rows inside a CTA
         if (W < 1) W = 1;
-        if (W > wmax) W = wmax;
+        if (W > 7) W = 7;                 // 7 restart warps + the producer = 256 threads, 255 registers each
+        // deepest ring (<= 4 stages) that still lets W restarts fit; otherwise fewer restarts per CTA
+        for (;;) {
+            S = 4;
+            while (S > 2 && 256 + (size_t)align_up(S * stage_bytes, 128) + (size_t)W * l.warp_stride > (size_t)smem_max) S--;
+            if (256 + (size_t)align_up(S * stage_bytes, 128) + (size_t)W * l.warp_stride <= (size_t)smem_max) break;
+            if (W == 1) return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: one restart plus the dense-row ring exceeds shared memory");
+            W--;
+        }
+        unsigned fixed = 256 + align_up(S * stage_bytes, 128);
         l.off_bar = 0;
         l.off_ring = 256;
         l.off_warp0 = fixed;
@@ -778,7 +962,8 @@ int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R,
 {
     if (R <= 0) return QCQP_OK;
     CdLayout L;
-    int rc = plan_layout(p, R, &L);
+    const int mode = (prm->strict == 1) ? MODE_STRICT : (prm->strict == 2 ? MODE_FRESH : MODE_GRAD);
+    int rc = plan_layout(p, R, mode == MODE_GRAD, &L);
     if (rc != QCQP_OK) return rc;
     const PackView& v = p->v;
     size_t fval_bytes = L.fval_smem ? 0 : (size_t)R * (v.m + 1) * 8;
@@ -792,7 +977,8 @@ int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R,
     int* ws_rel = (int*)((char*)p->ws + a1 + a2);
     CdK k;
     k.num_iters = prm->num_iters; k.viol_tol = prm->viol_tol; k.tol = prm->tol;
-    k.phase1 = prm->phase1; k.strict = prm->strict;
+    k.phase1 = prm->phase1;
+    k.mode = (mode == MODE_GRAD && !L.grad) ? MODE_FRESH : mode;   // no room for the cached row dots: fresh parallel dots
     k.refresh_every = prm->refresh_every > 0 ? prm->refresh_every : 64;
     QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int blocks = (R + L.W - 1) / L.W;

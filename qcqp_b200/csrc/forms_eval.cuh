@@ -100,12 +100,14 @@ __device__ __forceinline__ double eval_dense_form_seq(const PackView& P, int j, 
 // f_j(x) for j in [j0, j1], every result handed to sink(j, value) by exactly one lane.
 // Short sparse forms: one lane each.  Long sparse and dense forms: the whole warp (fast) or one lane (strict).
 template <class Sink>
-__device__ __forceinline__ void eval_forms(const PackView& P, const double* x, int j0, int j1, bool strict, int lane, Sink sink)
+__device__ __forceinline__ void eval_forms(const PackView& P, const double* x, int j0, int j1, bool strict, int lane, Sink sink,
+                                           bool skip_dense = false)
 {
     for (int base = j0; base <= j1; base += 32) {
         int j = base + lane;
         bool mine = j <= j1;
         bool dense = mine && P.dense_slot[j] >= 0;
+        if (dense && skip_dense) { mine = false; dense = false; }
         bool big = mine && !dense && (P.f_ptr[j + 1] - P.f_ptr[j]) > EVAL_LONG_FORM;
         if (mine && !dense && (!big || strict)) sink(j, eval_sparse_form_seq(P, j, x));
         if (mine && dense && strict) sink(j, eval_dense_form_seq(P, j, x));

@@ -112,6 +112,7 @@ class Pack:
     # ---- coordinate descent ----------------------------------------------------------------------------
     def cd_improve(self, X0, rng, num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, strict=False, refresh_every=0):
         """improve_coord_descent for each row of X0 (qcqp.py:181-192). rng: array of RngState, advanced in place.
+        strict: 0/False fast (cached dense row dots), 1/True bit-exact sequential dots, 2 fresh parallel dots.
         Returns (X, f0, maxviol, stats)."""
         X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, self.n)
         R = X0.shape[0]
@@ -119,7 +120,7 @@ class Pack:
             raise Exception("need one RNG state per restart")
         X = np.empty_like(X0); f0 = np.empty(R); mv = np.empty(R)
         stats = (CdStats * R)()
-        prm = CdParams(int(num_iters), float(viol_tol), float(tol), int(bool(phase1)), int(bool(strict)), int(refresh_every))
+        prm = CdParams(int(num_iters), float(viol_tol), float(tol), int(bool(phase1)), int(strict), int(refresh_every))
         check(_lib.load().qcqp_cd_improve(self._h, C.byref(prm), _ptr(X0), R, C.cast(rng, C.c_void_p), _ptr(X), _ptr(f0), _ptr(mv),
                                           C.cast(stats, C.c_void_p)))
         return X, f0, mv, stats

@@ -79,18 +79,31 @@ def test_cd_strict_matches_oracle(gen, gargs, R, kw):
         assert rel_close(vg[r], vo, rtol=1e-6, atol=1e-10)
 
 
-@pytest.mark.parametrize("gen,gargs,R", [
-    ("bls", dict(n=64, m=96, seed=1), 32),
-    ("bls", dict(n=200, m=300, seed=1), 16),
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("gen,gargs,R,kw", [
+    ("bls", dict(n=64, m=96, seed=1), 32, {}),
+    ("bls", dict(n=200, m=300, seed=1), 16, {}),
+    ("bls", dict(n=333, m=500, seed=5), 16, {}),          # odd n: padded rows
+    ("beam", dict(n=8, m=4, l=2, seed=1), 8, dict(num_iters=2)),   # dense constraints (n=16); short: the instance is chaotic
+    ("circle", dict(ncirc=8), 8, dict(num_iters=6)),
 ])
-def test_cd_fast_matches_oracle_1e6(gen, gargs, R):
-    """The production (fast) mode: warp-parallel fma row dots.  North-star bar: 1e-6 relative on (objective, max violation)."""
+def test_cd_fast_matches_oracle_1e6(gen, gargs, R, kw, mode):
+    """The production modes -- 0: cached dense row dots g = P x kept current by an axpy per move (default);
+    2: warp-parallel fma dot of the staged row at every step.  North-star bar: 1e-6 relative on (objective, max violation)."""
     forms, _ = GEN[gen](**gargs)
     n = forms[0][1].size
     rs = np.random.RandomState(7)
-    X0 = rs.randn(R, n)
+    X0 = rs.randn(R, n) if gen != "circle" else np.abs(rs.randn(R, n)) * 3 + 0.5
     seeds = 500 + np.arange(R)
-    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, seeds, False)
+    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, seeds, mode, **kw)
+    if gen == "beam":
+        # chaotic instance (DESIGN.md "conditioning"): the reference's own result moves by 1e-6 under a 1e-15 perturbation
+        # of x0, so only feasibility and descent are comparable across summation orders
+        from oracle import oracle as orc
+        P = orc.Problem(forms)
+        for r in range(R):
+            assert sg[r].status == 0 and (vg[r] < 1e-2 or vg[r] <= P.max_violation(X0[r]) + 1e-9)
+        return
     bad = 0
     for r in range(R):
         xo, fo, vo, so, st = out[r]

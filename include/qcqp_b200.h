@@ -97,7 +97,10 @@ typedef struct {
                                   move (the rows still stream through the TMA ring; the dot leaves the critical path).
                                1: strict -- every row dot summed sequentially in column order with separately rounded
                                   multiply/add, like SciPy's csr_matvec (bit-exact t1; slow).
-                               2: fresh -- warp-parallel fma dot of the staged row at every step. */
+                               2: fresh -- warp-parallel fma dot of the staged row at every step.
+                               3: the general kernel in fast mode even when the problem is separable (A/B measurements).
+                               With 0, separable problems (every constraint touches one coordinate, one constraint per
+                               coordinate: Boolean LS, MAXCUT) run the lane-per-coordinate kernel (csrc/cd_lpc.cu). */
     int32_t refresh_every;  /* recompute the cached f_j(x) from scratch every this many phase-2 sweeps; 0 = 64 */
 } qcqp_cd_params;
 

@@ -12,6 +12,7 @@
 // incremental update f_j += ... of the incident forms.
 #include <cstdio>
 
+#include "cd_shared.cuh"
 #include "common.cuh"
 #include "forms_eval.cuh"
 #include "onevar.cuh"
@@ -34,13 +35,7 @@ struct CdLayout {
     unsigned total;
 };
 
-enum { MODE_GRAD = 0, MODE_STRICT = 1, MODE_FRESH = 2 };
 
-struct CdK {
-    int num_iters;
-    double viol_tol, tol;
-    int phase1, mode, refresh_every;
-};
 
 struct WarpMem {
     double* x;
@@ -963,6 +958,13 @@ int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R,
     if (R <= 0) return QCQP_OK;
     CdLayout L;
     const int mode = (prm->strict == 1) ? MODE_STRICT : (prm->strict == 2 ? MODE_FRESH : MODE_GRAD);
+    if (prm->strict == 0 && p->lpc_ok) {
+        // separable problem (one single-coordinate constraint per coordinate): the lane-per-coordinate kernel
+        CdK k0;
+        k0.num_iters = prm->num_iters; k0.viol_tol = prm->viol_tol; k0.tol = prm->tol; k0.phase1 = prm->phase1; k0.mode = MODE_GRAD;
+        k0.refresh_every = prm->refresh_every > 0 ? prm->refresh_every : 16;
+        return lpc_launch(p, k0, dX0, R, drng, dX, df0, dmv, dstats, stream);
+    }
     int rc = plan_layout(p, R, mode == MODE_GRAD, &L);
     if (rc != QCQP_OK) return rc;
     const PackView& v = p->v;

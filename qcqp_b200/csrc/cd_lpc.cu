@@ -1,0 +1,401 @@
+// cd_lpc.cu -- coordinate descent for SEPARABLE problems: every constraint touches exactly one coordinate and every
+// coordinate has exactly one constraint (Boolean least squares, MAXCUT: x_k^2 = 1; any per-coordinate quadratic constraint).
+// Same algorithm and results as cd.cu (improve_coord_descent, qcqp.py:181-192), different parallel decomposition:
+// ONE WARP PER RESTART, ONE LANE PER COORDINATE, 32 consecutive coordinates per pass.
+//
+// Why that is legal.  For a separable problem the one-variable restriction of coordinate k's constraint is the constant
+// triple (P_j[k,k], q_j[k], r_j) -- t0 = f_j(z) = r_j exactly, as get_onevar_func computes it (utilities.py:99-105).
+//  * Phase 1 (qcqp.py:101-148) ignores the objective, so the steps of different coordinates do not interact at all except
+//    through (i) the order in which they consume the MT19937 stream and (ii) update_counter.  Whether a bisection probe is
+//    feasible does not depend on the random numbers, so each lane runs its whole bisection draw-free, counting the words
+//    the reference would consume (choice: one word iff two pieces; uniform: two); a warp scan turns the counts into
+//    stream offsets and every lane reads exactly the words of its LAST feasible probe -- the only draw that survives.
+//  * Phase 2 (qcqp.py:152-178): a step that does not move x_k changes nothing (x, f_0(x), g = P_0 x, the RNG), so 32 steps
+//    are evaluated speculatively from the same state; the steps before the first one that moves (or needs a random
+//    number) are committed wholesale, that one is applied (g += delta * column k: the only time a row of P_0 is read), and
+//    the pass restarts after it.  On Boolean LS ~3% of the steps move.
+// The objective's row dot comes from the cached g = P_0 x: (P_0 z)_k = g_k - P_0[k,k] x_k.
+#include "cd_shared.cuh"
+#include "common.cuh"
+#include "onevar.cuh"
+
+namespace qcqp {
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+// MT19937 state regeneration by the whole warp: chunks of 32 indices in order, each chunk read-then-write, which is
+// exactly the sequential recurrence (an index only ever needs older values at higher indices and newer ones >= 227 below).
+__device__ __forceinline__ void mt_refill_warp(uint32_t* mt, int lane)
+{
+    for (int base = 0; base < 624; base += 32) {
+        const int i = base + lane;
+        uint32_t nv = 0;
+        if (i < 624) {
+            const uint32_t a = mt[i], b = mt[(i + 1 == 624) ? 0 : i + 1], c = mt[(i + 397 >= 624) ? i + 397 - 624 : i + 397];
+            const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+            nv = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        __syncwarp();
+        if (i < 624) mt[i] = nv;
+        __syncwarp();
+    }
+}
+
+struct LpcMem {
+    double* x;
+    double* g;
+    uint32_t* mt;
+};
+
+// g = P_0 x and f_0(x) = x.g + q_0.x + r_0 from scratch
+__device__ __forceinline__ double lpc_refresh(const PackView& P, const LpcView& V, const LpcMem& w, int lane)
+{
+    const int n = P.n;
+    if (V.obj_dense) {
+        const int ld = P.ld;
+        const double* M = P.dense_P;   // the objective is dense slot 0
+        const int n2 = (n + 1) >> 1;
+        for (int c0 = 0; c0 < n2; c0 += 128) {
+            double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+            const int c = c0 + lane;
+            const bool v0 = c < n2, v1 = c + 32 < n2, v2 = c + 64 < n2, v3 = c + 96 < n2;
+            for (int r = 0; r < n; r++) {
+                const double xr = w.x[r];
+                const double2* row = reinterpret_cast<const double2*>(M + (size_t)r * ld);
+                if (v0) { const double2 t = row[c]; a0.x = fma(t.x, xr, a0.x); a0.y = fma(t.y, xr, a0.y); }
+                if (v1) { const double2 t = row[c + 32]; a1.x = fma(t.x, xr, a1.x); a1.y = fma(t.y, xr, a1.y); }
+                if (v2) { const double2 t = row[c + 64]; a2.x = fma(t.x, xr, a2.x); a2.y = fma(t.y, xr, a2.y); }
+                if (v3) { const double2 t = row[c + 96]; a3.x = fma(t.x, xr, a3.x); a3.y = fma(t.y, xr, a3.y); }
+            }
+            double2* g2 = reinterpret_cast<double2*>(w.g);
+            if (v0) g2[c] = a0;
+            if (v1) g2[c + 32] = a1;
+            if (v2) g2[c + 64] = a2;
+            if (v3) g2[c + 96] = a3;
+        }
+    } else {
+        for (int k = lane; k < n; k += 32) {
+            double s = V.o_diag[k] * w.x[k];
+            const int rb = V.o_rbeg[k], rl = V.o_rlen[k];
+            for (int t = rb; t < rb + rl; t++) s = fma(P.row_val[t], w.x[P.row_col[t]], s);
+            w.g[k] = s;
+        }
+    }
+    __syncwarp();
+    double acc = 0.0;
+    for (int k = lane; k < n; k += 32) acc = fma(w.x[k], w.g[k] + V.o_q[k], acc);
+    return warp_sum(acc) + V.o_r;
+}
+
+// max(prob.violations(x)) -- each constraint is (p x_k + q) x_k + r, the reference's own operation order
+__device__ __forceinline__ double lpc_max_violation(const PackView& P, const LpcView& V, const LpcMem& w, int lane)
+{
+    double mv = -QCQP_INF;
+    for (int k = lane; k < P.n; k += 32) {
+        const double v = violation_of(V.c_rel[k], onevar_eval(V.c_p[k], V.c_q[k], V.c_r[k], w.x[k]));
+        mv = (v > mv) ? v : mv;
+    }
+    return warp_max(mv);
+}
+
+// after x_k += delta: g += delta * (column k of P_0)
+__device__ __forceinline__ void lpc_axpy(const PackView& P, const LpcView& V, const LpcMem& w, int k, double delta, int lane)
+{
+    if (V.obj_dense) {
+        const int n2 = (P.n + 1) >> 1;
+        const double2* row = reinterpret_cast<const double2*>(P.dense_P + (size_t)k * P.ld);   // symmetric: row k == column k
+        double2* g2 = reinterpret_cast<double2*>(w.g);
+        for (int c = lane; c < n2; c += 32) {
+            const double2 rv = row[c];
+            double2 gv = g2[c];
+            gv.x = fma(rv.x, delta, gv.x);
+            gv.y = fma(rv.y, delta, gv.y);
+            g2[c] = gv;
+        }
+    } else {
+        if (lane == 0) w.g[k] = fma(V.o_diag[k], delta, w.g[k]);
+        const int rb = V.o_rbeg[k], rl = V.o_rlen[k];
+        for (int t = rb + lane; t < rb + rl; t += 32) {
+            const int c = P.row_col[t];
+            w.g[c] = fma(P.row_val[t], delta, w.g[c]);   // distinct columns within a row: no conflicts
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK prm, const double* __restrict__ X0, int R,
+                                                     qcqp_rng_state* rngs, double* __restrict__ X, double* __restrict__ f0_out,
+                                                     double* __restrict__ mv_out, qcqp_cd_stats* stats_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int n = P.n;
+    const int npad = (n + 1) & ~1;
+    const size_t rr = blockIdx.x;
+    if ((int)rr >= R) return;
+    LpcMem w;
+    w.x = reinterpret_cast<double*>(smem);
+    w.g = w.x + npad;
+    w.mt = reinterpret_cast<uint32_t*>(w.g + npad);
+
+    for (int i = lane; i < n; i += 32) w.x[i] = X0[rr * n + i];
+    if (lane == 0 && npad > n) { w.x[n] = 0.0; w.g[n] = 0.0; }
+    for (int i = lane; i < 624; i += 32) w.mt[i] = rngs[rr].key[i];
+    int pos = rngs[rr].pos;     // warp-uniform stream position
+    __syncwarp();
+
+    qcqp_cd_stats st;
+    st.steps_p1 = st.steps_p2 = st.updates_p1 = st.updates_p2 = st.steps_skipped = 0;
+    st.sweeps_p1 = st.sweeps_p2 = 0; st.status = QCQP_RUN_OK; st.ran_phase2 = 0;
+    const double tol = prm.tol, viol_tol = prm.viol_tol;
+    bool dead = false;
+
+    // =========================================== phase 1 ===========================================
+    if (prm.phase1) {
+        long long uc = 0;
+        double viol_last = QCQP_INF;
+        for (int t = 0; t < prm.num_iters && !dead; t++) {
+            if (viol_last < viol_tol) break;
+            st.sweeps_p1++;
+            bool skip = false;
+            const long long upd_before = st.updates_p1;
+            for (int k0 = 0; k0 < n && !skip && !dead;) {
+                const int B = (n - k0 < 32) ? (n - k0) : 32;
+                const bool act = lane < B;
+                const int k = k0 + lane;
+                double p = 0.0, q = 0.0, r = 0.0, xk = 0.0;
+                int rel = QCQP_RELOP_LE;
+                if (act) { p = V.c_p[k]; q = V.c_q[k]; r = V.c_r[k]; rel = V.c_rel[k]; xk = w.x[k]; }
+                // ---- draw-free bisection of this lane's coordinate (qcqp.py:113-131) ----
+                const double viol = violation_of(rel, onevar_eval(p, q, r, xk));
+                double ss = -tol, es = viol - viol_tol;
+                int words = 0, lastn = 0;
+                double l0 = 0.0, h0 = 0.0, l1 = 0.0, h1 = 0.0;
+                bool moved = false, hard = false;
+                if (act) {
+                    while (es - ss > tol) {
+                        const double s = (ss + es) / 2;
+                        double a0, b0, a1, b1;
+                        const int nC = single_constraint_pieces(p, q, r, rel, s, &a0, &b0, &a1, &b1);
+                        if (nC > 0) {
+                            words += (nC == 2) ? 3 : 2;     // choice(2) is exactly one masked word; uniform is two
+                            lastn = nC; l0 = a0; h0 = b0; l1 = a1; h1 = b1;
+                            moved = true;
+                            es = s;
+                            // an infinite bound makes np.random.uniform raise, possibly depending on the drawn piece:
+                            // such a coordinate is replayed with the real stream below
+                            if (is_inf(a0) || is_inf(b0) || (nC == 2 && (is_inf(a1) || is_inf(b1))) || nC > 2) hard = true;
+                        } else ss = s;
+                    }
+                }
+                // ---- update_counter in sequence order (qcqp.py:132-141) ----
+                const unsigned movedmask = __ballot_sync(FULL, act && moved);
+                const unsigned hardmask = __ballot_sync(FULL, act && hard);
+                const unsigned le = (lane == 31) ? FULL : ((2u << lane) - 1u);
+                const unsigned mm = movedmask & le;
+                const long long cval = moved ? 0 : (mm ? (long long)(lane - (31 - __clz(mm))) : uc + lane + 1);
+                const unsigned hit = __ballot_sync(FULL, act && !moved && cval == n);
+                int cut = B - 1;                                  // last lane committed in this pass
+                if (hit) cut = __ffs(hit) - 1;
+                const int firsthard = hardmask ? (__ffs(hardmask) - 1) : 32;
+                const bool do_hard = firsthard <= cut;
+                if (do_hard) cut = firsthard - 1;
+                const bool mine = act && lane <= cut;
+                // ---- stream offsets: words consumed by the committed coordinates before me ----
+                const int wmine = (mine && moved) ? words : 0;
+                int incl = wmine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                int rem_total = __shfl_sync(FULL, incl, 31);
+                const int cntlast = (lastn == 2) ? 3 : 2;
+                int need = (incl - wmine) + wmine - cntlast;      // relative position of my last probe's first word
+                uint32_t wd0 = 0, wd1 = 0, wd2 = 0;
+                int got = (wmine > 0) ? 0 : cntlast;              // words already fetched
+                for (;;) {
+                    const int avail = 624 - pos;
+                    while (got < cntlast && need + got < avail) {
+                        const uint32_t y = mt_temper(w.mt[pos + need + got]);
+                        if (got == 0) wd0 = y; else if (got == 1) wd1 = y; else wd2 = y;
+                        got++;
+                    }
+                    if (rem_total <= avail) { pos += rem_total; break; }
+                    __syncwarp();
+                    mt_refill_warp(w.mt, lane);
+                    need -= avail; rem_total -= avail; pos = 0;
+                }
+                if (wmine > 0) {
+                    // np.random.uniform(*C[np.random.choice(len(C))])   (utilities.py:266-267)
+                    const int idx = (lastn == 2) ? (int)(wd0 & 1u) : 0;
+                    const uint32_t ua = ((lastn == 2) ? wd1 : wd0) >> 5, ub = ((lastn == 2) ? wd2 : wd1) >> 6;
+                    const double dd = ((double)ua * 67108864.0 + (double)ub) / 9007199254740992.0;
+                    const double lo = idx ? l1 : l0, hi = idx ? h1 : h0;
+                    const double range = hi - lo;
+                    w.x[k] = lo + range * dd;
+                }
+                __syncwarp();
+                if (cut >= 0) {
+                    uc = __shfl_sync(FULL, cval, cut);
+                    st.steps_p1 += cut + 1;
+                    const unsigned cm = (cut == 31) ? FULL : ((2u << cut) - 1u);
+                    st.updates_p1 += __popc(movedmask & cm);
+                    if (hit && cut == __ffs(hit) - 1) skip = true;      // 'failed': the rest of the sweep is not executed
+                }
+                k0 += cut + 1;
+                if (do_hard && !skip) {
+                    // ---- one coordinate with the real stream (lane 0 draws), exactly the reference's loop ----
+                    const double hp = bcast(p, firsthard), hq = bcast(q, firsthard), hr = bcast(r, firsthard), hx = bcast(xk, firsthard);
+                    const int hrel = bcast_i(rel, firsthard);
+                    const double hv = violation_of(hrel, onevar_eval(hp, hq, hr, hx));
+                    double s2 = -tol, e2 = hv - viol_tol, nx = hx;
+                    bool mv2 = false;
+                    int err = 0;
+                    st.steps_p1++;
+                    while (e2 - s2 > tol && !err) {
+                        const double s = (s2 + e2) / 2;
+                        double cl[2], ch[2];
+                        const int nC = single_constraint_pieces(hp, hq, hr, hrel, s, &cl[0], &ch[0], &cl[1], &ch[1]);
+                        if (nC > 0) {
+                            double xv = 0.0;
+                            if (lane == 0) {
+                                MtRng rng;
+                                rng.key = w.mt; rng.pos = pos;
+                                choose_point(0.0, 0.0, 0.0, cl, ch, nC, rng, &xv, &err);
+                                pos = rng.pos;
+                            }
+                            pos = bcast_i(pos, 0); err = bcast_i(err, 0); nx = bcast(xv, 0);
+                            mv2 = true; e2 = s;
+                        } else s2 = s;
+                    }
+                    if (err) { st.status = err; dead = true; }
+                    else if (mv2) { if (lane == 0) w.x[k0] = nx; uc = 0; st.updates_p1++; }
+                    else { uc++; if (uc == n) skip = true; }
+                    __syncwarp();
+                    k0 += 1;
+                }
+            }
+            if (dead) break;
+            viol_last = lpc_max_violation(P, V, w, lane);      // qcqp.py:142
+            if (!skip && st.updates_p1 == upd_before && !(viol_last < viol_tol) && t + 1 < prm.num_iters) {
+                // fixed point: every remaining iteration of qcqp.py:110 repeats this no-op sweep (see cd.cu)
+                st.steps_skipped += (long long)(prm.num_iters - (t + 1)) * n;
+                break;
+            }
+        }
+    }
+
+    // =========================================== phase 2 ===========================================
+    double mv = lpc_max_violation(P, V, w, lane);              // improve_coord_descent's gate (qcqp.py:189)
+    if (!dead && mv < viol_tol) {
+        st.ran_phase2 = 1;
+        const double viol_p2 = mv;                               // frozen (qcqp.py:157)
+        double f0val = lpc_refresh(P, V, w, lane);
+        long long uc = 0;
+        bool done = false;
+        // per-lane memo of the constraint's pieces at the frozen level
+        double mp = 0.0, mq = 0.0, mr = 0.0, ml0 = 0.0, mh0 = 0.0, ml1 = 0.0, mh1 = 0.0;
+        int mrel = -1, mnC = 0;
+        for (int t = 0; t < prm.num_iters && !done; t++) {
+            st.sweeps_p2++;
+            for (int k0 = 0; k0 < n && !done;) {
+                const int B = (n - k0 < 32) ? (n - k0) : 32;
+                const bool act = lane < B;
+                const int k = k0 + lane;
+                double xk = 0.0, p0 = 0.0, q0 = 0.0, r0 = f0val, xi = 0.0;
+                int rc = 0;
+                if (act) {
+                    const double p = V.c_p[k], q = V.c_q[k], r = V.c_r[k];
+                    const int rel = V.c_rel[k];
+                    xk = w.x[k];
+                    if (!(mrel == rel && mp == p && mq == q && mr == r)) {
+                        mnC = single_constraint_pieces(p, q, r, rel, viol_p2, &ml0, &mh0, &ml1, &mh1);
+                        mp = p; mq = q; mr = r; mrel = rel;
+                    }
+                    if (V.o_inc[k]) {
+                        // obj = f0.get_onevar_func(x, k): t2 = P0[k,k], t1 = 2 (P0 z)_k + q0[k], t0 = f0(x) - x_k (t2 x_k + t1)
+                        p0 = V.o_diag[k];
+                        q0 = 2 * (w.g[k] - p0 * xk) + V.o_q[k];
+                        r0 = f0val - xk * (p0 * xk + q0);
+                    }
+                    rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
+                }
+                const bool wants_move = act && rc == 1 && fabs(xi - xk) > tol;
+                const unsigned stop = __ballot_sync(FULL, wants_move || (act && rc == 2));
+                const int first = stop ? (__ffs(stop) - 1) : B;
+                // the `first` steps before it change nothing: update_counter += 1 each (qcqp.py:172-176)
+                if ((long long)n - uc <= first) { st.steps_p2 += (n - uc); done = true; break; }   // converged inside the run
+                uc += first;
+                st.steps_p2 += first;
+                if (first == B) { k0 += B; continue; }
+                // ---- the coordinate that moves or needs a random number ----
+                const int kf = k0 + first;
+                const double fx = bcast(xk, first), fp0 = bcast(p0, first), fq0 = bcast(q0, first), fr0 = bcast(r0, first);
+                double fxi = bcast(xi, first);
+                const int frc = bcast_i(rc, first);
+                st.steps_p2++;
+                bool found = true;
+                if (frc == 2) {
+                    double cl[2], ch[2];
+                    cl[0] = bcast(ml0, first); ch[0] = bcast(mh0, first); cl[1] = bcast(ml1, first); ch[1] = bcast(mh1, first);
+                    const int nC = bcast_i(mnC, first);
+                    int err = 0, fnd = 0;
+                    double xv = 0.0;
+                    if (lane == 0) {
+                        MtRng rng;
+                        rng.key = w.mt; rng.pos = pos;
+                        fnd = choose_point(fp0, fq0, fr0, cl, ch, nC, rng, &xv, &err);
+                        pos = rng.pos;
+                    }
+                    pos = bcast_i(pos, 0); err = bcast_i(err, 0); fnd = bcast_i(fnd, 0); fxi = bcast(xv, 0);
+                    if (err) { st.status = err; dead = true; done = true; break; }
+                    found = fnd != 0;
+                }
+                if (found && fabs(fxi - fx) > tol) {
+                    if (lane == 0) w.x[kf] = fxi;
+                    f0val = fr0 + fxi * (fp0 * fxi + fq0);        // f_0(x) = t0 + b (t2 b + t1)
+                    lpc_axpy(P, V, w, kf, fxi - fx, lane);
+                    uc = 0;
+                    st.updates_p2++;
+                } else {
+                    uc++;
+                    if (uc == n) { done = true; break; }
+                }
+                k0 = kf + 1;
+            }
+            if (!done && prm.refresh_every > 0 && ((t + 1) % prm.refresh_every) == 0) f0val = lpc_refresh(P, V, w, lane);
+        }
+    }
+
+    // ---------------- results (qcqp.py:415-417) ----------------
+    const double f0fin = lpc_refresh(P, V, w, lane);
+    mv = lpc_max_violation(P, V, w, lane);
+    for (int i = lane; i < n; i += 32) X[rr * n + i] = w.x[i];
+    for (int i = lane; i < 624; i += 32) rngs[rr].key[i] = w.mt[i];
+    if (lane == 0) {
+        rngs[rr].pos = pos;
+        f0_out[rr] = f0fin;
+        mv_out[rr] = mv;
+        if (stats_out) stats_out[rr] = st;
+    }
+}
+
+int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0, double* dmv,
+               qcqp_cd_stats* dstats, cudaStream_t stream)
+{
+    const int n = p->v.n;
+    const int npad = (n + 1) & ~1;
+    size_t smem = (size_t)2 * npad * 8 + 624 * 4;
+    if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: n too large for the separable kernel");
+    QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_lpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, dX0, R, drng, dX, df0, dmv, dstats);
+    QCQP_CUDA_TRY(cudaGetLastError());
+    return QCQP_OK;
+}
+
+}  // namespace qcqp

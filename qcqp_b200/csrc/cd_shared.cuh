@@ -1,0 +1,18 @@
+// cd_shared.cuh -- parameters shared by the two coordinate-descent kernels (cd.cu: general; cd_lpc.cu: separable problems)
+#pragma once
+#include "common.cuh"
+
+namespace qcqp {
+
+enum { MODE_GRAD = 0, MODE_STRICT = 1, MODE_FRESH = 2, MODE_GRAD_GENERAL = 3 };
+
+struct CdK {
+    int num_iters;
+    double viol_tol, tol;
+    int phase1, mode, refresh_every;
+};
+
+int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0, double* dmv,
+               qcqp_cd_stats* dstats, cudaStream_t stream);
+
+}  // namespace qcqp

@@ -73,6 +73,24 @@ struct PackView {
     const double* eig_qhat;    // [m][n]
 };
 
+// Separable view (cd_lpc.cu): every constraint touches exactly one coordinate and every coordinate has exactly one
+// constraint (Boolean least squares, MAXCUT, any per-coordinate quadratic constraint).  Then the one-variable restriction of
+// coordinate k's constraint is the constant triple (c_p[k], c_q[k], c_r[k]) -- t0 = f_j(z) = r_j exactly, as the reference
+// computes it -- and coordinates are independent of each other in phase 1.
+struct LpcView {
+    const double* c_p;     // [n] P_j[k,k]
+    const double* c_q;     // [n] q_j[k]
+    const double* c_r;     // [n] r_j
+    const int* c_rel;      // [n] relop_j
+    const double* o_diag;  // [n] P_0[k,k]
+    const double* o_q;     // [n] q_0[k]
+    const int* o_rbeg;     // [n] objective row k (off-diagonal) in row_col/row_val; unused when the objective is dense
+    const int* o_rlen;     // [n]
+    const unsigned char* o_inc;  // [n] 1 when the objective involves x_k structurally
+    double o_r;
+    int obj_dense;
+};
+
 }  // namespace qcqp
 
 // the opaque handle of the C ABI
@@ -89,6 +107,8 @@ struct qcqp_pack {
     size_t io_bytes;
     bool has_eig;
     int objective_dense;
+    bool lpc_ok;
+    qcqp::LpcView lpc;
 };
 
 namespace qcqp {

@@ -73,3 +73,13 @@ extern "C" int qcqp_shim_choice(qcqp_rng_state* st, int32_t n)
     st->pos = rng.pos;
     return v;
 }
+
+// separable case: pieces of a single constraint + the RNG-free part of the minimiser choice (cd_lpc.cu)
+extern "C" int qcqp_shim_single_det(const double* f0, const double* f, int32_t relop, double s, double* xout, double* pieces4, int32_t* nC)
+{
+    double lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    int c = single_constraint_pieces(f[0], f[1], f[2], relop, s, &lo0, &hi0, &lo1, &hi1);
+    pieces4[0] = lo0; pieces4[1] = hi0; pieces4[2] = lo1; pieces4[3] = hi1;
+    *nC = c;
+    return choose_point_det(f0[0], f0[1], f0[2], lo0, hi0, lo1, hi1, c, xout);
+}

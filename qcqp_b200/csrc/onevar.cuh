@@ -359,4 +359,52 @@ QCQP_HD int choose_point(double p, double q, double r, const double* c_lo, const
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// One constraint standing alone (the separable case: every coordinate has exactly one constraint that touches only it).
+// Feasible pieces at level s, at most two, returned in registers.
+// ---------------------------------------------------------------------------------------------------------
+QCQP_HD int single_constraint_pieces(double p, double q, double r, int rel, double s, double* lo0, double* hi0, double* lo1,
+                                     double* hi1)
+{
+    Fold f;
+    f.init();
+    f.mcnt = 1;
+    Ival I[2];
+    I[0].lo = I[0].hi = I[1].lo = I[1].hi = 0.0;
+    const int c = feasible_intervals(p, q, r, rel, s, I);
+    if (c == 0) return 0;
+    if (c == 1) f.add_single(I[0].lo, I[0].hi);
+    double cl[4], ch[4];
+    cl[0] = cl[1] = ch[0] = ch[1] = 0.0;
+    const int nC = sweep_small8(f, c == 2, I[0], I[1], cl, ch);
+    *lo0 = cl[0]; *hi0 = ch[0]; *lo1 = cl[1]; *hi1 = ch[1];
+    return nC;
+}
+
+// The part of choose_point that needs no random number, for at most two pieces:
+//   0 = None, 1 = *xout found deterministically, 2 = the reference would draw (flat objective or tied endpoints).
+QCQP_HD int choose_point_det(double p, double q, double r, double lo0, double hi0, double lo1, double hi1, int nC, double* xout)
+{
+    if (nC == 0) return 0;
+    if (p == 0.0 && q == 0.0) return 2;
+    const bool two = (nC == 2);
+    if (p > 0.0) {
+        const double x0 = -q / (2. * p);
+        if ((lo0 <= x0 && x0 <= hi0) || (two && lo1 <= x0 && x0 <= hi1)) { *xout = x0; return 1; }
+    }
+    const double v0 = onevar_eval(p, q, r, lo0), v1 = onevar_eval(p, q, r, hi0);
+    const double v2 = two ? onevar_eval(p, q, r, lo1) : QCQP_INF, v3 = two ? onevar_eval(p, q, r, hi1) : QCQP_INF;
+    double bestf = QCQP_INF;
+    if (v0 < bestf) bestf = v0;
+    if (v1 < bestf) bestf = v1;
+    if (v2 < bestf) bestf = v2;
+    if (v3 < bestf) bestf = v3;
+    const bool m0 = (v0 == bestf), m1 = (v1 == bestf), m2 = two && (v2 == bestf), m3 = two && (v3 == bestf);
+    const int cnt = (int)m0 + (int)m1 + (int)m2 + (int)m3;
+    if (cnt == 0) return 0;
+    if (cnt > 1) return 2;
+    *xout = m0 ? lo0 : (m1 ? hi0 : (m2 ? lo1 : hi1));
+    return 1;
+}
+
 }  // namespace qcqp

@@ -252,7 +252,8 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     qcqp_pack* p = new qcqp_pack();
     std::memset(&p->v, 0, sizeof(p->v));
     std::memset(&p->info, 0, sizeof(p->info));
-    p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->has_eig = false;
+    p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->has_eig = false; p->lpc_ok = false;
+    std::memset(&p->lpc, 0, sizeof(p->lpc));
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;
     PackView& v = p->v;
@@ -271,6 +272,52 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     UP(r, r); UP(relop, relop); UP(dense_slot, dense_slot); UP(dense_form, dense_form); UP(dense_P, dense_P);
 #undef UP
     if (rc != QCQP_OK) { qcqp_pack_destroy(p); return rc; }
+
+    // ---- separable view for the lane-per-coordinate kernel (cd_lpc.cu) ----------------------------------------
+    {
+        bool ok = (m == n);
+        std::vector<double> c_p(n, 0.0), c_q(n, 0.0), c_r(n, 0.0), o_diag(n, 0.0), o_q(n, 0.0);
+        std::vector<int> c_rel(n, 0), c_seen(n, 0), o_rbeg(n, 0), o_rlen(n, 0);
+        std::vector<unsigned char> o_inc(n, 0);
+        for (int j = 1; j < nf && ok; j++) {
+            int64_t a = d->p_ptr[j], b = d->p_ptr[j + 1], qa = d->q_ptr[j], qb = d->q_ptr[j + 1];
+            if (dense_slot[j] >= 0 || b - a > 1 || qb - qa > 1 || (b - a == 0 && qb - qa == 0)) { ok = false; break; }
+            int k = (b > a) ? d->p_row[a] : d->q_idx[qa];
+            if (b > a && d->p_col[a] != k) { ok = false; break; }
+            if (qb > qa && d->q_idx[qa] != k) { ok = false; break; }
+            if (c_seen[k]) { ok = false; break; }
+            c_seen[k] = 1;
+            c_p[k] = (b > a) ? d->p_val[a] : 0.0;
+            c_q[k] = (qb > qa) ? d->q_val[qa] : 0.0;
+            c_r[k] = d->r[j];
+            c_rel[k] = d->relop[j];
+            if (c_p[k] == 0.0 && c_q[k] == 0.0) ok = false;
+        }
+        for (int k = 0; k < n && ok; k++) if (!c_seen[k]) ok = false;
+        if (ok) {
+            for (int k = 0; k < n; k++) {
+                int e = inc_ptr[k];
+                if (e < inc_ptr[k + 1] && (inc_form[e] & INC_FORM_MASK) == 0) {
+                    o_inc[k] = 1; o_diag[k] = inc_t2[e]; o_q[k] = inc_qk[e];
+                    o_rbeg[k] = row_ptr[e]; o_rlen[k] = row_len[e];
+                }
+            }
+            LpcView& L = p->lpc;
+            L.o_r = d->r[0];
+            L.obj_dense = dense_slot[0] >= 0;
+            if (rc == QCQP_OK) rc = upload(p, c_p, &L.c_p);
+            if (rc == QCQP_OK) rc = upload(p, c_q, &L.c_q);
+            if (rc == QCQP_OK) rc = upload(p, c_r, &L.c_r);
+            if (rc == QCQP_OK) rc = upload(p, c_rel, &L.c_rel);
+            if (rc == QCQP_OK) rc = upload(p, o_diag, &L.o_diag);
+            if (rc == QCQP_OK) rc = upload(p, o_q, &L.o_q);
+            if (rc == QCQP_OK) rc = upload(p, o_rbeg, &L.o_rbeg);
+            if (rc == QCQP_OK) rc = upload(p, o_rlen, &L.o_rlen);
+            if (rc == QCQP_OK) rc = upload(p, o_inc, &L.o_inc);
+            if (rc != QCQP_OK) { qcqp_pack_destroy(p); return rc; }
+        }
+        p->lpc_ok = ok;
+    }
 
     // ---- info: the algorithmic bytes of one restart-sweep, streaming model of SURVEY.md 8d --------------------
     //   sum over dense forms (8 n^2 + 8 n) + 12 nnz_offdiag(sparse) + 20 INC + 16 (m+1) + 16 n

@@ -79,8 +79,10 @@ def test_cd_strict_matches_oracle(gen, gargs, R, kw):
         assert rel_close(vg[r], vo, rtol=1e-6, atol=1e-10)
 
 
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode", [0, 2, 3])
 @pytest.mark.parametrize("gen,gargs,R,kw", [
+    ("bls", dict(n=10, m=15, seed=1), 16, {}),
+    ("bls", dict(n=33, m=50, seed=2), 16, {}),
     ("bls", dict(n=64, m=96, seed=1), 32, {}),
     ("bls", dict(n=200, m=300, seed=1), 16, {}),
     ("bls", dict(n=333, m=500, seed=5), 16, {}),          # odd n: padded rows
@@ -88,8 +90,10 @@ def test_cd_strict_matches_oracle(gen, gargs, R, kw):
     ("circle", dict(ncirc=8), 8, dict(num_iters=6)),
 ])
 def test_cd_fast_matches_oracle_1e6(gen, gargs, R, kw, mode):
-    """The production modes -- 0: cached dense row dots g = P x kept current by an axpy per move (default);
-    2: warp-parallel fma dot of the staged row at every step.  North-star bar: 1e-6 relative on (objective, max violation)."""
+    """The production modes -- 0 (default): separable problems (Boolean LS here) run the lane-per-coordinate kernel
+    cd_lpc.cu, others the general kernel with cached dense row dots; 3: the general kernel with cached row dots even for
+    separable problems; 2: warp-parallel fma dot of the staged row at every step.
+    North-star bar: 1e-6 relative on (objective, max violation); stream positions and step counts must also agree."""
     forms, _ = GEN[gen](**gargs)
     n = forms[0][1].size
     rs = np.random.RandomState(7)
@@ -108,8 +112,46 @@ def test_cd_fast_matches_oracle_1e6(gen, gargs, R, kw, mode):
     for r in range(R):
         xo, fo, vo, so, st = out[r]
         ok = rel_close(fg[r], fo, rtol=1e-6, atol=1e-9) and rel_close(vg[r], vo, rtol=1e-6, atol=1e-9)
+        ok = ok and rng_g[r].pos == st.pos and (sg[r].steps_p1, sg[r].steps_p2, sg[r].steps_skipped) == (so.steps_p1, so.steps_p2, so.steps_skipped)
         bad += (not ok)
     assert bad == 0, "%d of %d restarts differ from the oracle beyond 1e-6" % (bad, R)
+
+
+def test_cd_separable_kernel_edge_cases():
+    """cd_lpc.cu: stream refills inside a pass (long phase-1 bisections), phase1=False, tiny n, the stuck-coordinate
+    fast-forward, and a MAXCUT instance (flat objectives and ties go through the real stream)."""
+    from oracle import oracle as orc
+    from qcqp_b200 import engine
+    # far-away starts: ~20 probes per coordinate -> several MT19937 refills per 32-coordinate pass
+    forms, _ = GEN["bls"](n=100, m=150, seed=3)
+    rs = np.random.RandomState(9)
+    X0 = rs.randn(12, 100) * 300.0
+    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, 40 + np.arange(12), 0)
+    for r in range(12):
+        xo, fo, vo, so, st = out[r]
+        assert rng_g[r].pos == st.pos and (sg[r].steps_p1, sg[r].steps_p2) == (so.steps_p1, so.steps_p2)
+        assert rel_close(fg[r], fo, rtol=1e-6) and rel_close(vg[r], vo, rtol=1e-6, atol=1e-10)
+    # phase1=False from a nearly feasible point; n smaller than a warp
+    forms, _ = GEN["bls"](n=7, m=12, seed=1)
+    X0 = np.sign(rs.randn(6, 7)) * np.sqrt(1 + 4e-3 * rs.rand(6, 7))
+    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, 70 + np.arange(6), 0, phase1=False)
+    for r in range(6):
+        xo, fo, vo, so, st = out[r]
+        assert rng_g[r].pos == st.pos and sg[r].steps_p2 == so.steps_p2 and rel_close(fg[r], fo, rtol=1e-9)
+    # stuck coordinate: fast-forward
+    forms, _ = GEN["bls"](n=40, m=60, seed=1)
+    x0 = np.ones(40); x0[17] = np.sqrt(1.01005)
+    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, x0[None, :], [5], 0, num_iters=30)
+    assert sg[0].steps_skipped == out[0][3].steps_skipped > 0 and sg[0].steps_p1 == out[0][3].steps_p1 and np.array_equal(Xg[0], out[0][0])
+    # MAXCUT: not bit-comparable in fast mode (SURVEY H5), but every run must end feasible with a sensible cut
+    forms, info = GEN["maxcut"](n=60, p=0.1, seed=1)
+    pack = engine.Pack(forms)
+    X0 = rs.randn(32, 60)
+    Xg, fg, vg, sg = pack.cd_improve(X0, engine.rng_states(seeds=np.arange(32)), num_iters=40)
+    Xs, fs, vs, ss = pack.cd_improve(X0, engine.rng_states(seeds=np.arange(32)), num_iters=40, strict=1)
+    assert all(s.status == 0 for s in sg) and vg.max() < 1e-2
+    assert abs(np.mean(-fg) - np.mean(-fs)) < 0.05 * abs(np.mean(-fs))
+    pack.close()
 
 
 def test_cd_error_statuses():

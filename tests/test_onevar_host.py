@@ -28,6 +28,8 @@ def shim():
     L.qcqp_shim_uniform.argtypes = [C.c_void_p, C.c_double, C.c_double]
     L.qcqp_shim_choice.restype = C.c_int
     L.qcqp_shim_choice.argtypes = [C.c_void_p, C.c_int32]
+    L.qcqp_shim_single_det.restype = C.c_int
+    L.qcqp_shim_single_det.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -117,3 +119,38 @@ def test_device_rng_transforms(shim):
             else:
                 n = [1, 2, 3, 5, 8, 200][t % 6]
                 assert int(rs.choice(n)) == shim.qcqp_shim_choice(C.byref(st), n)
+
+
+def test_device_single_constraint_deterministic_choice(shim):
+    """The separable fast path (cd_lpc.cu): with one constraint, the RNG-free decision either equals onevar_qcqp's result with
+    the RNG untouched, or reports 'needs a draw' exactly when the reference draws."""
+    rs = np.random.RandomState(77)
+    for t in range(6000):
+        kind = rs.randint(0, 7)
+        if kind == 6:
+            p, q, r = float(rs.randint(-2, 3)), float(rs.randint(-2, 3)), float(rs.randint(-4, 2))
+        else:
+            p = rs.randn() * (kind != 0) * (1e-5 if kind == 5 else 1.0); q = rs.randn() * (kind != 1); r = rs.randn() - 1.0
+        if p == 0 and q == 0:
+            q = 1.0
+        rel = "==" if rs.rand() < 0.5 else "<="
+        k0 = rs.randint(0, 5)
+        f0 = (float(abs(rs.randn())) if k0 == 0 else (0.0 if k0 in (1, 2) else float(rs.randint(-2, 3))),
+              0.0 if k0 == 2 else float(rs.randint(-3, 4)) if k0 == 4 else float(rs.randn()), float(rs.randn() * 10 ** rs.randint(0, 6)))
+        s = float(rs.choice([0.0, 1e-4, 0.01, 0.3, 1.0, 2.5]) * (1 if t % 2 else abs(rs.randn())))
+        st = orc.RngState.from_seed(t)
+        pos0 = st.pos
+        try:
+            want = orc.onevar_qcqp(f0, [(p, q, r, rel)], s, st)
+            err = False
+        except OverflowError:
+            err = True
+        f0a = np.array(f0); fa = np.array([p, q, r]); out = C.c_double(); pieces = np.zeros(4); nC = C.c_int32()
+        rc = shim.qcqp_shim_single_det(f0a.ctypes.data, fa.ctypes.data, orc.RELOP_CODE[rel], s, C.byref(out), pieces.ctypes.data, C.byref(nC))
+        drew = err or st.pos != pos0
+        if rc == 2:
+            assert drew or (f0[0] == 0 and f0[1] == 0), (t, f0, (p, q, r, rel), s)
+        elif rc == 1:
+            assert not drew and want == out.value, (t, f0, (p, q, r, rel), s, want, out.value)
+        else:
+            assert want is None and not drew, (t, f0, (p, q, r, rel), s, want)

@@ -66,7 +66,26 @@ __device__ __forceinline__ double lpc_refresh(const PackView& P, const LpcView& 
             double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
             const int c = c0 + lane;
             const bool v0 = c < n2, v1 = c + 32 < n2, v2 = c + 64 < n2, v3 = c + 96 < n2;
-            for (int r = 0; r < n; r++) {
+            const double2 zz = make_double2(0.0, 0.0);
+            int r = 0;
+            for (; r + 4 <= n; r += 4) {
+                double2 t[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double2* row = reinterpret_cast<const double2*>(M + (size_t)(r + u) * ld);
+                    t[u][0] = v0 ? __ldg(&row[c]) : zz; t[u][1] = v1 ? __ldg(&row[c + 32]) : zz;
+                    t[u][2] = v2 ? __ldg(&row[c + 64]) : zz; t[u][3] = v3 ? __ldg(&row[c + 96]) : zz;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double xr = w.x[r + u];
+                    a0.x = fma(t[u][0].x, xr, a0.x); a0.y = fma(t[u][0].y, xr, a0.y);
+                    a1.x = fma(t[u][1].x, xr, a1.x); a1.y = fma(t[u][1].y, xr, a1.y);
+                    a2.x = fma(t[u][2].x, xr, a2.x); a2.y = fma(t[u][2].y, xr, a2.y);
+                    a3.x = fma(t[u][3].x, xr, a3.x); a3.y = fma(t[u][3].y, xr, a3.y);
+                }
+            }
+            for (; r < n; r++) {
                 const double xr = w.x[r];
                 const double2* row = reinterpret_cast<const double2*>(M + (size_t)r * ld);
                 if (v0) { const double2 t = row[c]; a0.x = fma(t.x, xr, a0.x); a0.y = fma(t.y, xr, a0.y); }
@@ -112,12 +131,21 @@ __device__ __forceinline__ void lpc_axpy(const PackView& P, const LpcView& V, co
         const int n2 = (P.n + 1) >> 1;
         const double2* row = reinterpret_cast<const double2*>(P.dense_P + (size_t)k * P.ld);   // symmetric: row k == column k
         double2* g2 = reinterpret_cast<double2*>(w.g);
-        for (int c = lane; c < n2; c += 32) {
-            const double2 rv = row[c];
-            double2 gv = g2[c];
-            gv.x = fma(rv.x, delta, gv.x);
-            gv.y = fma(rv.y, delta, gv.y);
-            g2[c] = gv;
+        // the row comes from L2 once per move: put 8 independent 16-byte loads in flight before the first use
+        for (int c0 = lane; c0 < n2; c0 += 256) {
+            double2 rv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) rv[u] = (c0 + 32 * u < n2) ? __ldg(&row[c0 + 32 * u]) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int c = c0 + 32 * u;
+                if (c < n2) {
+                    double2 gv = g2[c];
+                    gv.x = fma(rv[u].x, delta, gv.x);
+                    gv.y = fma(rv[u].y, delta, gv.y);
+                    g2[c] = gv;
+                }
+            }
         }
     } else {
         if (lane == 0) w.g[k] = fma(V.o_diag[k], delta, w.g[k]);
@@ -393,6 +421,16 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     size_t smem = (size_t)2 * npad * 8 + 624 * 4;
     if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: n too large for the separable kernel");
     QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_lpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        // one warp per CTA: only ceil(R / #SM) CTAs are ever resident on an SM, so carve out just their shared memory and
+        // leave the rest of the 228 KB to L1 -- the per-coordinate constants and the rows of P_0 are re-read through it
+        const int per_sm = (R + num_sms(p->device) - 1) / num_sms(p->device);
+        const double need = (double)per_sm * (double)(smem + 1024);
+        int pct = (int)(100.0 * need / (228.0 * 1024.0)) + 1;
+        if (pct < 10) pct = 10;
+        if (pct > 100) pct = 100;
+        QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_lpc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, dX0, R, drng, dX, df0, dmv, dstats);
     QCQP_CUDA_TRY(cudaGetLastError());
     return QCQP_OK;

@@ -105,6 +105,9 @@ struct qcqp_pack {
     // device staging arena of the host-buffer entry points (grow-only, so steady-state calls do not cudaMalloc)
     void* io;
     size_t io_bytes;
+    // scratch of the batched eval / SDR sampler (row-dot partials, device-generated normals)
+    void* ws2;
+    size_t ws2_bytes;
     bool has_eig;
     int objective_dense;
     bool lpc_ok;
@@ -115,6 +118,7 @@ namespace qcqp {
 
 int ensure_workspace(qcqp_pack* p, size_t bytes);
 int ensure_io(qcqp_pack* p, size_t bytes);
+int ensure_workspace2(qcqp_pack* p, size_t bytes);
 int num_sms(int device);
 int max_smem_optin(int device);
 

@@ -41,10 +41,74 @@ __global__ void eval_kernel(PackView P, const double* __restrict__ X, int R, dou
     }
 }
 
+int gemm_quadform_launch(int S, int n, const double* dX, const double* dPj, int ld, double* dpart, cudaStream_t stream);
+int gemm_col_blocks(int n);
+
+// Batched path for packs with dense forms: x_s' P_j x_s of every dense form as a tiled FP64 GEMM with a row-dot epilogue
+// (gemm.cu), then this kernel -- one warp per point -- adds q_j.x + r_j, evaluates the sparse forms and reduces.
+__global__ void eval_finish_kernel(PackView P, const double* __restrict__ X, int R, const double* __restrict__ part, int ncb,
+                                   double* __restrict__ f0, double* __restrict__ maxviol, double* __restrict__ viol)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int n = P.n, m = P.m;
+    double* x = reinterpret_cast<double*>(smem) + (size_t)warp * ((n + 1) & ~1);
+    for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) x[i] = X[(size_t)r * n + i];
+        __syncwarp();
+        double mv = -QCQP_INF, fobj = 0.0;
+        const PackView& Pr = P;
+        double* vrow = viol ? viol + (size_t)r * m : nullptr;
+        auto sink = [&](int j, double v) {
+            if (j == 0) fobj = v;
+            else {
+                double vv = violation_of(Pr.relop[j], v);
+                if (vrow) vrow[j - 1] = vv;
+                mv = (vv > mv) ? vv : mv;
+            }
+        };
+        eval_forms(P, x, 0, m, false, lane, sink, /*skip_dense=*/true);
+        for (int d = 0; d < P.n_dense; d++) {
+            const int j = P.dense_form[d];
+            double acc = 0.0;
+            for (long long e = P.q_ptr[j] + lane; e < P.q_ptr[j + 1]; e += 32) acc = fma(P.q_val[e], x[P.q_idx[e]], acc);
+            acc = warp_sum(acc);
+            double quad = 0.0;
+            for (int cb = 0; cb < ncb; cb++) quad += part[((size_t)d * ncb + cb) * R + r];   // fixed order: reproducible
+            if (lane == 0) sink(j, quad + acc + P.r[j]);
+        }
+        mv = warp_max(mv);
+        fobj = warp_sum(fobj);
+        if (lane == 0) {
+            f0[r] = fobj;
+            maxviol[r] = (m > 0) ? mv : 0.0;
+        }
+    }
+}
+
 int eval_launch(qcqp_pack* p, const double* dX, int R, double* df0, double* dmv, double* dviol, cudaStream_t stream)
 {
     if (R <= 0) return QCQP_OK;
     const int n = p->v.n;
+    if (p->v.n_dense > 0 && R >= 32) {
+        const int nd = p->v.n_dense, ncb = gemm_col_blocks(n), ld = p->v.ld;
+        int rc = ensure_workspace2(p, (size_t)nd * ncb * R * 8);
+        if (rc != QCQP_OK) return rc;
+        double* part = (double*)p->ws2;
+        for (int d = 0; d < nd; d++) {
+            rc = gemm_quadform_launch(R, n, dX, p->v.dense_P + (size_t)d * n * ld, ld, part + (size_t)d * ncb * R, stream);
+            if (rc != QCQP_OK) return rc;
+        }
+        const int wpb = 4;
+        size_t smem = (size_t)wpb * ((n + 1) & ~1) * 8;
+        if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_eval: n too large for the shared-memory staging of x");
+        QCQP_CUDA_TRY(cudaFuncSetAttribute(eval_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_finish_kernel<<<(R + wpb - 1) / wpb, wpb * 32, smem, stream>>>(p->v, dX, R, part, ncb, df0, dmv, dviol);
+        QCQP_CUDA_TRY(cudaGetLastError());
+        return QCQP_OK;
+    }
     const int wpb = 4;
     size_t smem = (size_t)wpb * ((n + 1) & ~1) * 8;
     if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_eval: n too large for the shared-memory staging of x");

@@ -44,6 +44,19 @@ int ensure_workspace(qcqp_pack* p, size_t bytes)
     return QCQP_OK;
 }
 
+int ensure_workspace2(qcqp_pack* p, size_t bytes)
+{
+    if (bytes <= p->ws2_bytes) return QCQP_OK;
+    if (p->ws2) cudaFree(p->ws2);
+    p->ws2 = nullptr;
+    p->ws2_bytes = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&p->ws2, want);
+    if (e != cudaSuccess) return fail(QCQP_ERR_NOMEM, std::string("eval workspace cudaMalloc: ") + cudaGetErrorString(e));
+    p->ws2_bytes = want;
+    return QCQP_OK;
+}
+
 int ensure_io(qcqp_pack* p, size_t bytes)
 {
     if (bytes <= p->io_bytes) return QCQP_OK;
@@ -94,6 +107,7 @@ extern "C" void qcqp_pack_destroy(qcqp_pack* p)
     for (void* d : p->allocs) cudaFree(d);
     if (p->ws) cudaFree(p->ws);
     if (p->io) cudaFree(p->io);
+    if (p->ws2) cudaFree(p->ws2);
     delete p;
 }
 
@@ -252,7 +266,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     qcqp_pack* p = new qcqp_pack();
     std::memset(&p->v, 0, sizeof(p->v));
     std::memset(&p->info, 0, sizeof(p->info));
-    p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->has_eig = false; p->lpc_ok = false;
+    p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->ws2 = nullptr; p->ws2_bytes = 0; p->has_eig = false; p->lpc_ok = false;
     std::memset(&p->lpc, 0, sizeof(p->lpc));
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;

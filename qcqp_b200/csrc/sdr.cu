@@ -94,11 +94,45 @@ __global__ void sdr_kernel(PackView P, const double* __restrict__ mu, const doub
     }
 }
 
+int gemm_sdr_launch(int S, int n, const double* dZ, const double* dF, const double* dmu, double* dX, cudaStream_t stream);
+int eval_launch(qcqp_pack* p, const double* dX, int R, double* df0, double* dmv, double* dviol, cudaStream_t stream);
+
+// standard normals for the batched path when the caller supplies none: the same Philox stream as sdr_kernel
+__global__ void philox_normals_kernel(uint64_t seed, int S, int n, double* __restrict__ Z)
+{
+    const int pairs = (n + 1) / 2;
+    const long long total = (long long)S * pairs;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / pairs), pr = (int)(i % pairs);
+        double a, b;
+        philox_normal2(seed, (uint64_t)s, (uint32_t)pr, &a, &b);
+        Z[(size_t)s * n + 2 * pr] = a;
+        if (2 * pr + 1 < n) Z[(size_t)s * n + 2 * pr + 1] = b;
+    }
+}
+
 int sdr_launch(qcqp_pack* p, const double* dmu, const double* dF, const double* dZ, uint64_t seed, int S, double* dX, double* df0,
                double* dmv, cudaStream_t stream)
 {
     if (S <= 0) return QCQP_OK;
     const int n = p->v.n;
+    if (S >= 32) {
+        // batched path: X = Z F + mu as a tiled FP64 GEMM (gemm.cu), then the batched evaluation
+        if (!dZ) {
+            // dX doubles as the buffer of the normals? No: the GEMM reads Z while writing X.  Stage Z behind the eval scratch.
+            double* zbuf = nullptr;
+            cudaError_t e = cudaMallocAsync((void**)&zbuf, (size_t)S * n * 8, stream);
+            if (e != cudaSuccess) return fail(QCQP_ERR_NOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+            philox_normals_kernel<<<296, 256, 0, stream>>>(seed, S, n, zbuf);
+            int rc = gemm_sdr_launch(S, n, zbuf, dF, dmu, dX, stream);
+            cudaFreeAsync(zbuf, stream);
+            if (rc != QCQP_OK) return rc;
+        } else {
+            int rc = gemm_sdr_launch(S, n, dZ, dF, dmu, dX, stream);
+            if (rc != QCQP_OK) return rc;
+        }
+        return eval_launch(p, dX, S, df0, dmv, nullptr, stream);
+    }
     const int wpb = 4;
     size_t smem = (size_t)wpb * 2 * ((n + 1) & ~1) * 8;
     if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_sdr_sample_eval: n too large for shared-memory staging");

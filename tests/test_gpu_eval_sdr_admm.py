@@ -82,8 +82,10 @@ def test_sdr_device_rng_statistics():
     assert np.abs(X.mean(0) - mu).max() < 0.03
     C = np.cov(X.T)
     assert np.abs(C - F.T.dot(F)).max() < 0.05
-    X2, _, _ = pack.sdr_sample_eval(mu, F, Z=None, S=16, seed=7)
-    assert np.array_equal(X2, X[:16])      # counter-based: a draw depends only on (seed, index)
+    X2, _, _ = pack.sdr_sample_eval(mu, F, Z=None, S=64, seed=7)
+    assert np.array_equal(X2, X[:64])      # counter-based: a draw depends only on (seed, index)
+    X3, _, _ = pack.sdr_sample_eval(mu, F, Z=None, S=16, seed=7)      # small batches take the warp-per-draw kernel
+    assert np.allclose(X3, X[:16], rtol=1e-12, atol=1e-13)
     f_chk, v_chk = pack.eval(X[:50])
     assert rel_close(f0[:50], f_chk, rtol=1e-12) and rel_close(mv[:50], v_chk, rtol=1e-12, atol=1e-12)
     pack.close()

@@ -287,10 +287,12 @@ def run_own(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_bytes / t_cd / 1e9
         traffic = None
+        kname = "qcqp::cd_lpc_kernel" if info.separable else "qcqp::cd_kernel"
         tpath = os.path.join(ROOT, "profiles", "cd_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch") if tj.get("kernel") == kname else None
             except Exception:
                 traffic = None
         cpu = None
@@ -322,9 +324,11 @@ def run_own(args):
                        "kernel_ms": {"sdr_sample_eval": float(np.mean(sdr_ms)), "cd_improve": float(np.mean(cd_ms))},
                        "device_vs_host_api_agree": agree, "wall_s_timed_loop": wall},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "qcqp::cd_kernel", "peak_source": peak_src,
-                         "model": "algorithmic streaming bytes (SURVEY 8d): phase-2 sweep %.0f B, phase-1 sweep %.0f B per restart; "
-                                  "no credit for the CTA-level sharing of staged P rows" % (info.bytes_per_sweep_phase2, info.bytes_per_sweep_phase1)},
+                         "kernel": kname, "peak_source": peak_src,
+                         "model": "algorithmic streaming bytes (SURVEY 8d): phase-2 sweep %.0f B, phase-1 sweep %.0f B per restart, i.e. "
+                                  "every form read once per restart-sweep.  The kernel reads a row of P0 only when its coordinate moves "
+                                  "(cached g = P0 x), so frac > 1 means fewer bytes than the model, not skipped sweeps; `traffic` is the "
+                                  "measured DRAM bytes per launch (P0 is L2-resident)" % (info.bytes_per_sweep_phase2, info.bytes_per_sweep_phase1)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_sweeps / e2e_time, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_time},

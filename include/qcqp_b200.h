@@ -77,6 +77,8 @@ typedef struct {
     int64_t device_bytes;   /* HBM held by the pack */
     double bytes_per_sweep_phase2; /* algorithmic bytes of one restart-sweep, streaming model */
     double bytes_per_sweep_phase1; /* same without the objective (phase 1 never reads P_0) */
+    int32_t separable;      /* 1: every constraint touches one coordinate, one constraint per coordinate -> cd_lpc kernel */
+    int32_t pad_;
 } qcqp_pack_info;
 
 /* NumPy RandomState (MT19937) state, field for field: np.random.get_state() -> (key, pos, has_gauss, cached_gaussian) */

@@ -23,7 +23,8 @@ class PackDesc(C.Structure):
 class PackInfo(C.Structure):
     _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("n_dense", C.c_int32), ("max_incidence", C.c_int32),
                 ("incidences", C.c_int64), ("nnz_offdiag", C.c_int64), ("device_bytes", C.c_int64),
-                ("bytes_per_sweep_phase2", C.c_double), ("bytes_per_sweep_phase1", C.c_double)]
+                ("bytes_per_sweep_phase2", C.c_double), ("bytes_per_sweep_phase1", C.c_double),
+                ("separable", C.c_int32), ("pad_", C.c_int32)]
 
 
 class RngState(C.Structure):

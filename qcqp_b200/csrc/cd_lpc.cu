@@ -131,13 +131,14 @@ __device__ __forceinline__ void lpc_axpy(const PackView& P, const LpcView& V, co
         const int n2 = (P.n + 1) >> 1;
         const double2* row = reinterpret_cast<const double2*>(P.dense_P + (size_t)k * P.ld);   // symmetric: row k == column k
         double2* g2 = reinterpret_cast<double2*>(w.g);
-        // the row comes from L2 once per move: put 8 independent 16-byte loads in flight before the first use
-        for (int c0 = lane; c0 < n2; c0 += 256) {
-            double2 rv[8];
+        // the row comes from L2 once per move: put 16 independent 16-byte loads in flight (a whole row for n <= 1024)
+        // before the first use, so a move costs one L2 round trip
+        for (int c0 = lane; c0 < n2; c0 += 512) {
+            double2 rv[16];
 #pragma unroll
-            for (int u = 0; u < 8; u++) rv[u] = (c0 + 32 * u < n2) ? __ldg(&row[c0 + 32 * u]) : make_double2(0.0, 0.0);
+            for (int u = 0; u < 16; u++) rv[u] = (c0 + 32 * u < n2) ? __ldg(&row[c0 + 32 * u]) : make_double2(0.0, 0.0);
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < 16; u++) {
                 const int c = c0 + 32 * u;
                 if (c < n2) {
                     double2 gv = g2[c];
@@ -158,9 +159,13 @@ __device__ __forceinline__ void lpc_axpy(const PackView& P, const LpcView& V, co
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK prm, const double* __restrict__ X0, int R,
-                                                     qcqp_rng_state* rngs, double* __restrict__ X, double* __restrict__ f0_out,
-                                                     double* __restrict__ mv_out, qcqp_cd_stats* stats_out)
+// stage 0: the whole of improve_coord_descent in one launch.
+// stage 1: phase 1 only (x, stream and stats are written back).   stage 2: phase 2 only, starting from stage 1's output with
+// g = P_0 x supplied in G (one tiled GEMM for all restarts instead of one latency-bound GEMV per warp); the returned
+// (f0, maxviol) then come from the batched eval kernels.
+__global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK prm, int stage, const double* __restrict__ X0, int R,
+                                                     qcqp_rng_state* rngs, double* X, const double* __restrict__ G,
+                                                     double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x;
@@ -173,7 +178,10 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
     w.g = w.x + npad;
     w.mt = reinterpret_cast<uint32_t*>(w.g + npad);
 
-    for (int i = lane; i < n; i += 32) w.x[i] = X0[rr * n + i];
+    {
+        const double* src = (stage == 2) ? X : X0;
+        for (int i = lane; i < n; i += 32) w.x[i] = src[rr * n + i];
+    }
     if (lane == 0 && npad > n) { w.x[n] = 0.0; w.g[n] = 0.0; }
     for (int i = lane; i < 624; i += 32) w.mt[i] = rngs[rr].key[i];
     int pos = rngs[rr].pos;     // warp-uniform stream position
@@ -184,9 +192,13 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
     st.sweeps_p1 = st.sweeps_p2 = 0; st.status = QCQP_RUN_OK; st.ran_phase2 = 0;
     const double tol = prm.tol, viol_tol = prm.viol_tol;
     bool dead = false;
+    if (stage == 2) {
+        st = stats_out[rr];
+        dead = st.status != QCQP_RUN_OK;
+    }
 
     // =========================================== phase 1 ===========================================
-    if (prm.phase1) {
+    if (prm.phase1 && stage != 2) {
         long long uc = 0;
         double viol_last = QCQP_INF;
         for (int t = 0; t < prm.num_iters && !dead; t++) {
@@ -318,12 +330,29 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
         }
     }
 
+    if (stage == 1) {
+        for (int i = lane; i < n; i += 32) X[rr * n + i] = w.x[i];
+        for (int i = lane; i < 624; i += 32) rngs[rr].key[i] = w.mt[i];
+        if (lane == 0) { rngs[rr].pos = pos; stats_out[rr] = st; }
+        return;
+    }
+
     // =========================================== phase 2 ===========================================
     double mv = lpc_max_violation(P, V, w, lane);              // improve_coord_descent's gate (qcqp.py:189)
     if (!dead && mv < viol_tol) {
         st.ran_phase2 = 1;
         const double viol_p2 = mv;                               // frozen (qcqp.py:157)
-        double f0val = lpc_refresh(P, V, w, lane);
+        double f0val;
+        if (stage == 2) {
+            // g = P_0 x of this restart, computed for all restarts by one GEMM; f_0(x) = x.g + q_0.x + r_0
+            const double* gr = G + rr * (size_t)npad;
+            double acc = 0.0;
+            for (int k = lane; k < n; k += 32) { const double gk = gr[k]; w.g[k] = gk; acc = fma(w.x[k], gk + V.o_q[k], acc); }
+            f0val = warp_sum(acc) + V.o_r;
+            __syncwarp();
+        } else {
+            f0val = lpc_refresh(P, V, w, lane);
+        }
         long long uc = 0;
         bool done = false;
         // per-lane memo of the constraint's pieces at the frozen level
@@ -401,10 +430,14 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
     }
 
     // ---------------- results (qcqp.py:415-417) ----------------
-    const double f0fin = lpc_refresh(P, V, w, lane);
-    mv = lpc_max_violation(P, V, w, lane);
     for (int i = lane; i < n; i += 32) X[rr * n + i] = w.x[i];
     for (int i = lane; i < 624; i += 32) rngs[rr].key[i] = w.mt[i];
+    if (stage == 2) {
+        if (lane == 0) { rngs[rr].pos = pos; stats_out[rr] = st; }
+        return;                                                  // (f0, maxviol): batched eval kernels, launched next
+    }
+    const double f0fin = lpc_refresh(P, V, w, lane);
+    mv = lpc_max_violation(P, V, w, lane);
     if (lane == 0) {
         rngs[rr].pos = pos;
         f0_out[rr] = f0fin;
@@ -412,6 +445,9 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
         if (stats_out) stats_out[rr] = st;
     }
 }
+
+int eval_launch(qcqp_pack* p, const double* dX, int R, double* df0, double* dmv, double* dviol, cudaStream_t stream);
+int gemm_plain_launch(int M, int N, int K, const double* dA, int lda, const double* dB, int ldb, double* dC, int ldc, cudaStream_t stream);
 
 int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0, double* dmv,
                qcqp_cd_stats* dstats, cudaStream_t stream)
@@ -431,7 +467,22 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
         if (pct > 100) pct = 100;
         QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_lpc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, dX0, R, drng, dX, df0, dmv, dstats);
+    if (p->lpc.obj_dense && R >= 64) {
+        // phase 1 -> G = X P_0 (tiled GEMM) -> phase 2 -> batched (f0, maxviol)
+        const size_t gbytes = ((size_t)R * npad * 8 + 255) & ~(size_t)255;
+        int rc = ensure_workspace(p, gbytes + (size_t)R * sizeof(qcqp_cd_stats));
+        if (rc != QCQP_OK) return rc;
+        double* G = (double*)p->ws;
+        qcqp_cd_stats* stats = dstats ? dstats : (qcqp_cd_stats*)((char*)p->ws + gbytes);
+        cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 1, dX0, R, drng, dX, nullptr, df0, dmv, stats);
+        QCQP_CUDA_TRY(cudaGetLastError());
+        rc = gemm_plain_launch(R, n, n, dX, n, p->v.dense_P, p->v.ld, G, npad, stream);
+        if (rc != QCQP_OK) return rc;
+        cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 2, dX0, R, drng, dX, G, df0, dmv, stats);
+        QCQP_CUDA_TRY(cudaGetLastError());
+        return eval_launch(p, dX, R, df0, dmv, nullptr, stream);
+    }
+    cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 0, dX0, R, drng, dX, nullptr, df0, dmv, dstats);
     QCQP_CUDA_TRY(cudaGetLastError());
     return QCQP_OK;
 }

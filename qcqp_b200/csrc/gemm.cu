@@ -114,6 +114,15 @@ int gemm_quadform_launch(int S, int n, const double* dX, const double* dPj, int 
     return QCQP_OK;
 }
 
+// C = A B, no epilogue extras
+int gemm_plain_launch(int M, int N, int K, const double* dA, int lda, const double* dB, int ldb, double* dC, int ldc, cudaStream_t stream)
+{
+    dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
+    dgemm_tile_kernel<EPI_BIAS_STORE><<<grid, 256, 0, stream>>>(M, N, K, dA, lda, dB, ldb, nullptr, dC, ldc, nullptr, 0, nullptr);
+    QCQP_CUDA_TRY(cudaGetLastError());
+    return QCQP_OK;
+}
+
 int gemm_col_blocks(int n) { return (n + GB_N - 1) / GB_N; }
 
 }  // namespace qcqp

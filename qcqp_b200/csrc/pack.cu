@@ -331,6 +331,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
             if (rc != QCQP_OK) { qcqp_pack_destroy(p); return rc; }
         }
         p->lpc_ok = ok;
+        p->info.separable = ok ? 1 : 0;
     }
 
     // ---- info: the algorithmic bytes of one restart-sweep, streaming model of SURVEY.md 8d --------------------

@@ -87,9 +87,12 @@ class ClockSampler:
 
 
 def build_problem():
-    from qcqp_b200 import problems as pb
+    """The C2 instance and its SDP relaxation solution X* (host solve, outside every timed region -- the reference
+    caches it too, qcqp.py:390-395)."""
+    from qcqp_b200 import problems as pb, relax
+    from qcqp_b200.forms import QCQPForm
     forms, _ = pb.boolean_least_squares(N_VAR, M_ROWS, seed=1)
-    Xstar = pb.synthetic_sdr_solution(N_VAR, rank=16, seed=5)   # declared synthetic stand-in for the host SDP
+    Xstar, _bound = relax.solve_sdr(QCQPForm.from_tuples(forms))
     return forms, Xstar
 
 
@@ -316,7 +319,7 @@ def run_own(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "restarts_per_gpu": R, "n": N_VAR, "m": N_VAR, "num_iters": 1000, "viol_tol": 1e-2,
                        "tol": 1e-4, "rng": "MT19937 stream per restart (np.random.seed(1000 + r))",
-                       "sdr_solution": "synthetic X* = V V^T, V = randn(1001, 16) row-normalised (no SDP solver in the image)",
+                       "sdr_solution": "X* of the SDP relaxation, host solve by qcqp_b200/relax.py (unit-diagonal mixing method), untimed",
                        "l2": "flushed between timed iterations (384 MiB memset outside the event brackets)",
                        "sweeps_per_step": {"phase1": sweeps_p1, "phase2": sweeps_p2,
                                            "phase2_max_per_restart": int(st["w2"].max()), "phase2_mean_per_restart": float(st["w2"].mean()),

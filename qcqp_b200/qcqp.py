@@ -16,6 +16,7 @@ import scipy.sparse as sp
 
 from . import settings as s
 from . import engine
+from . import relax
 from .forms import QCQPForm, QuadraticFunction
 
 log = logging.getLogger("qcqp_b200")   # the reference opens ./qcqp.log at import time (qcqp.py:39); this package does not
@@ -115,23 +116,29 @@ class QCQP:
             return self._assign(X, f0, mv)
         if method == s.SPECTRAL:
             if self.spectral_sol is None:
-                raise Exception("The spectral relaxation needs an SDP solve (solve_spectral, qcqp.py:41-70), which stays on the "
-                                "host and is out of scope of this engine; set qcqp.spectral_sol / spectral_bound yourself.")
+                # host SDP, as in the reference (qcqp.py:384-387); solver kwargs (iters, tol) are forwarded
+                self.spectral_sol, self.spectral_bound = relax.solve_spectral(self.qcqp_form, *args, **kwargs)
+                if self.maximize_flag:
+                    self.spectral_bound *= -1
             X = np.asarray(self.spectral_sol, dtype=np.float64).reshape(1, self.n)
             f0, mv = self._pack.eval(X)
             return self._assign(X, f0, mv)
         # SDR
+        corrected = bool(kwargs.pop("corrected", False))
+        device_rng = kwargs.pop("device_rng", False)
+        seed = int(kwargs.pop("seed", 0))
         if self.sdr_sol is None:
             if "sdr_solution" in kwargs:
                 self.set_sdr_solution(kwargs.pop("sdr_solution"), kwargs.pop("sdr_bound", None))
             else:
-                raise Exception("The SDP relaxation (solve_sdr, qcqp.py:72-97) stays on the host and no SDP solver is bundled: "
-                                "call qcqp.set_sdr_solution(X) or pass sdr_solution=X.")
+                # host SDP, as in the reference (qcqp.py:390-393): qcqp_b200.relax (NumPy) since cvxpy/SCS are not required
+                self.sdr_sol, self.sdr_bound = relax.solve_sdr(self.qcqp_form, *args, **kwargs)
+                if self.maximize_flag:
+                    self.sdr_bound *= -1
         if self.mu is None:
-            self.mu, self.Sigma, self._F = engine.sdr_factor(self.sdr_sol, eps=eps, corrected=bool(kwargs.pop("corrected", False)))
-        device_rng = kwargs.pop("device_rng", False)
+            self.mu, self.Sigma, self._F = engine.sdr_factor(self.sdr_sol, eps=eps, corrected=corrected)
         if device_rng:
-            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=None, S=S, seed=int(kwargs.pop("seed", 0)))
+            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=None, S=S, seed=seed)
         else:
             # np.random.multivariate_normal draws standard_normal(n) per sample from the global stream (SURVEY a-7)
             Z = np.stack([np.random.standard_normal(self.n) for _ in range(S)])

@@ -146,3 +146,33 @@ def test_gloo_world_size_2_best_pick(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "OK %d" % r in o, o
+
+
+def test_host_relaxations():
+    """qcqp_b200/relax.py (host NumPy SDP, setup code): the unit-diagonal mixing method agrees with the general ADMM solver,
+    solutions are PSD and feasible, and the values are valid bounds."""
+    import itertools
+    from qcqp_b200 import relax, problems as pb
+    from qcqp_b200.forms import QCQPForm
+    forms, _ = pb.maxcut(12, 0.4, seed=3)
+    F = QCQPForm.from_tuples(forms)
+    X1, v1 = relax.solve_sdr(F)
+    N = 13
+    E = np.zeros((N, N)); E[-1, -1] = 1
+    A_eq = [E] + [relax.homogeneous_form(f) for f in F.fs]
+    X2, v2, info = relax._admm_sdp(relax.homogeneous_form(F.f0), A_eq, [1.0] + [0.0] * 12, [], [])
+    assert abs(v1 - v2) < 1e-4 * abs(v1)
+    assert np.linalg.eigvalsh(X1).min() > -1e-9 and np.abs(np.diag(X1) - 1).max() < 1e-9
+    forms, _ = pb.boolean_least_squares(8, 12, seed=2)
+    F = QCQPForm.from_tuples(forms)
+    X, v = relax.solve_sdr(F)
+    P0 = np.asarray(forms[0][0].todense()); q0 = forms[0][1]; r0 = forms[0][2]
+    best = min(np.array(s) @ P0 @ np.array(s) + q0 @ np.array(s) + r0 for s in itertools.product([-1.0, 1.0], repeat=8))
+    assert v <= best + 1e-6
+    xs, vs = relax.solve_spectral(F)
+    assert vs <= v + 1e-5
+    forms, _ = pb.beamforming(6, 3, 2, seed=1)
+    F = QCQPForm.from_tuples(forms)
+    X, v = relax.solve_sdr(F)
+    assert np.linalg.eigvalsh(X).min() > -1e-7 and abs(X[-1, -1] - 1) < 1e-6
+    assert max(np.sum(relax.homogeneous_form(f) * X) for f in F.fs) < 1e-4

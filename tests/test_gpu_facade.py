@@ -80,5 +80,28 @@ def test_facade_errors():
         qc.suggest(Q.RANDOM); qc.improve(Q.DCCP)
     with pytest.raises(Exception, match="PyIpopt package is not installed"):
         qc.improve(Q.IPOPT)
-    with pytest.raises(Exception, match="SDP"):
-        Q.QCQP(forms).suggest(Q.SDR)
+
+
+def test_suggest_sdr_and_spectral_with_the_host_relaxation():
+    """examples/boolean_least_squares.py / maxcut.py end to end with the bundled host SDP (qcqp_b200/relax.py):
+    the relaxation value bounds every point the improve step returns."""
+    import itertools
+    import qcqp_b200 as Q
+    from qcqp_b200 import problems as pb
+    forms, _ = pb.boolean_least_squares(10, 15, seed=1)
+    qc = Q.QCQP(forms)
+    np.random.seed(1)
+    qc.suggest(Q.SDR)
+    assert qc.sdr_sol.shape == (11, 11) and abs(qc.sdr_sol[-1, -1] - 1) < 1e-9
+    f_cd, v_cd = qc.improve(Q.COORD_DESCENT)
+    P0 = np.asarray(forms[0][0].todense()); q0 = forms[0][1]; r0 = forms[0][2]
+    best = min(np.array(s) @ P0 @ np.array(s) + q0 @ np.array(s) + r0 for s in itertools.product([-1.0, 1.0], repeat=10))
+    assert qc.sdr_bound <= best + 1e-6 and qc.sdr_bound <= f_cd + 1e-3 and v_cd < 1e-2
+    f_sp, v_sp = qc.suggest(Q.SPECTRAL)
+    assert qc.spectral_bound <= qc.sdr_bound + 1e-6
+    forms, info = pb.maxcut(25, 0.2, seed=1)
+    qm = Q.QCQP(forms, maximize=True)
+    np.random.seed(1)
+    qm.suggest(Q.SDR, samples=32)
+    f, v = qm.improve(Q.COORD_DESCENT, seed=3, num_iters=50)
+    assert f <= qm.sdr_bound + 1e-3 and v < 1e-2      # SDR-based upper bound on the cut

@@ -52,6 +52,7 @@ struct LpcMem {
     double* x;
     double* g;
     uint32_t* mt;
+    double* blk;   // [32][32] diagonal block of P_0 for the pass in flight (dense objective only)
 };
 
 // g = P_0 x and f_0(x) = x.g + q_0.x + r_0 from scratch
@@ -159,6 +160,47 @@ __device__ __forceinline__ void lpc_axpy(const PackView& P, const LpcView& V, co
     __syncwarp();
 }
 
+// Dense objective, end of a 32-coordinate pass: g += sum over the coordinates that moved (bit m of `moved`: x_{k0+m} += the
+// delta held by lane m) of delta * row of P_0.  Two whole rows (2 x 16 sixteen-byte loads per lane for n <= 1024) are in
+// flight at a time, so a pass pays one L2 round trip per pair of moves instead of one per move and column chunk.
+__device__ __forceinline__ void lpc_axpy_multi(const PackView& P, const LpcMem& w, int k0, unsigned moved, double mydelta, int lane)
+{
+    const int n2 = (P.n + 1) >> 1;
+    double2* g2 = reinterpret_cast<double2*>(w.g);
+    const double2 zz = make_double2(0.0, 0.0);
+    unsigned mm = moved;
+    while (mm) {
+        const int m0 = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int m1 = mm ? (__ffs(mm) - 1) : -1;
+        if (mm) mm &= mm - 1;
+        const double d0 = __shfl_sync(FULL, mydelta, m0);
+        const double d1 = __shfl_sync(FULL, mydelta, m1 < 0 ? 0 : m1);
+        const double2* r0 = reinterpret_cast<const double2*>(P.dense_P + (size_t)(k0 + m0) * P.ld);
+        const double2* r1 = reinterpret_cast<const double2*>(P.dense_P + (size_t)(k0 + (m1 < 0 ? m0 : m1)) * P.ld);
+        for (int cb = 0; cb < n2; cb += 512) {
+            double2 a[16], b[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int c = cb + lane + 32 * u;
+                a[u] = (c < n2) ? __ldg(&r0[c]) : zz;
+                b[u] = (c < n2 && m1 >= 0) ? __ldg(&r1[c]) : zz;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int c = cb + lane + 32 * u;
+                if (c < n2) {
+                    double2 gv = g2[c];
+                    gv.x = fma(a[u].x, d0, gv.x); gv.y = fma(a[u].y, d0, gv.y);
+                    gv.x = fma(b[u].x, d1, gv.x); gv.y = fma(b[u].y, d1, gv.y);
+                    g2[c] = gv;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // stage 0: the whole of improve_coord_descent in one launch.
 // stage 1: phase 1 only (x, stream and stats are written back).   stage 2: phase 2 only, starting from stage 1's output with
 // g = P_0 x supplied in G (one tiled GEMM for all restarts instead of one latency-bound GEMV per warp); the returned
@@ -177,6 +219,7 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
     w.x = reinterpret_cast<double*>(smem);
     w.g = w.x + npad;
     w.mt = reinterpret_cast<uint32_t*>(w.g + npad);
+    w.blk = reinterpret_cast<double*>(w.mt + 624);
 
     {
         const double* src = (stage == 2) ? X : X0;
@@ -360,7 +403,96 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
         int mrel = -1, mnC = 0;
         for (int t = 0; t < prm.num_iters && !done; t++) {
             st.sweeps_p2++;
-            for (int k0 = 0; k0 < n && !done;) {
+            // ---- dense objective: blocked Gauss-Seidel.  All moves inside a 32-coordinate pass are resolved in registers with
+            // the 32 x 32 diagonal block of P_0 (one coalesced fetch per pass); the rest of g is brought up to date once, after
+            // the pass, with the rows of every coordinate that moved in flight together. ----
+            for (int k0 = 0; V.obj_dense && k0 < n && !done; k0 += 32) {
+                const int B = (n - k0 < 32) ? (n - k0) : 32;
+                const bool act = lane < B;
+                const int k = k0 + lane;
+                double xk = 0.0, p0 = 0.0, oq = 0.0, gl = 0.0, q0 = 0.0, r0 = f0val, xi = 0.0, mydelta = 0.0;
+                int rc = 0;
+                if (act) {
+                    const double p = V.c_p[k], q = V.c_q[k], r = V.c_r[k];
+                    const int rel = V.c_rel[k];
+                    xk = w.x[k];
+                    if (!(mrel == rel && mp == p && mq == q && mr == r)) {
+                        mnC = single_constraint_pieces(p, q, r, rel, viol_p2, &ml0, &mh0, &ml1, &mh1);
+                        mp = p; mq = q; mr = r; mrel = rel;
+                    }
+                    p0 = V.o_diag[k]; oq = V.o_q[k]; gl = w.g[k];
+                    q0 = 2 * (gl - p0 * xk) + oq;
+                    r0 = f0val - xk * (p0 * xk + q0);
+                    rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
+                }
+                // diagonal block D[i][j] = P_0[k0+i][k0+j], fetched only when the pass has a candidate mover:
+                // iteration i loads row i coalesced (lane = column)
+                if (__ballot_sync(FULL, act && (rc == 2 || (rc == 1 && fabs(xi - xk) > tol)))) {
+                    const double* base = P.dense_P + (size_t)k0 * P.ld + k0;
+                    double dv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) dv[i] = (i < B && act) ? __ldg(base + (size_t)i * P.ld + lane) : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) w.blk[i * 32 + lane] = dv[i];
+                }
+                __syncwarp();
+                unsigned moved = 0;
+                int cur = 0;            // next coordinate of the pass to resolve
+                while (cur < B) {
+                    const bool pending = act && lane >= cur;
+                    const bool wants_move = pending && rc == 1 && fabs(xi - xk) > tol;
+                    const unsigned stop = __ballot_sync(FULL, wants_move || (pending && rc == 2));
+                    const int first = stop ? (__ffs(stop) - 1) : B;
+                    const int quiet = first - cur;      // steps that change nothing (qcqp.py:172-176)
+                    if ((long long)n - uc <= quiet) { st.steps_p2 += (n - uc); done = true; break; }
+                    uc += quiet;
+                    st.steps_p2 += quiet;
+                    if (first == B) break;
+                    const double fx = bcast(xk, first), fp0 = bcast(p0, first), fq0 = bcast(q0, first), fr0 = bcast(r0, first);
+                    double fxi = bcast(xi, first);
+                    const int frc = bcast_i(rc, first);
+                    st.steps_p2++;
+                    bool found = true;
+                    if (frc == 2) {
+                        double cl[2], ch[2];
+                        cl[0] = bcast(ml0, first); ch[0] = bcast(mh0, first); cl[1] = bcast(ml1, first); ch[1] = bcast(mh1, first);
+                        const int nC = bcast_i(mnC, first);
+                        int err = 0, fnd = 0;
+                        double xv = 0.0;
+                        if (lane == 0) {
+                            MtRng rng;
+                            rng.key = w.mt; rng.pos = pos;
+                            fnd = choose_point(fp0, fq0, fr0, cl, ch, nC, rng, &xv, &err);
+                            pos = rng.pos;
+                        }
+                        pos = bcast_i(pos, 0); err = bcast_i(err, 0); fnd = bcast_i(fnd, 0); fxi = bcast(xv, 0);
+                        if (err) { st.status = err; dead = true; done = true; break; }
+                        found = fnd != 0;
+                    }
+                    if (found && fabs(fxi - fx) > tol) {
+                        const double delta = fxi - fx;
+                        if (lane == first) { w.x[k] = fxi; mydelta = delta; }
+                        moved |= 1u << first;
+                        f0val = fr0 + fxi * (fp0 * fxi + fq0);        // f_0(x) = t0 + b (t2 b + t1)
+                        uc = 0;
+                        st.updates_p2++;
+                        // the coordinates still to come see the move through their own entry of column `first`
+                        if (act && lane > first) {
+                            gl = fma(w.blk[first * 32 + lane], delta, gl);     // D[lane][first] = D[first][lane]
+                            q0 = 2 * (gl - p0 * xk) + oq;
+                            r0 = f0val - xk * (p0 * xk + q0);
+                            rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
+                        }
+                    } else {
+                        uc++;
+                        if (uc == n) { done = true; break; }
+                    }
+                    cur = first + 1;
+                }
+                if (done) break;
+                if (moved) lpc_axpy_multi(P, w, k0, moved, mydelta, lane);
+            }
+            for (int k0 = 0; !V.obj_dense && k0 < n && !done;) {
                 const int B = (n - k0 < 32) ? (n - k0) : 32;
                 const bool act = lane < B;
                 const int k = k0 + lane;
@@ -454,7 +586,7 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
 {
     const int n = p->v.n;
     const int npad = (n + 1) & ~1;
-    size_t smem = (size_t)2 * npad * 8 + 624 * 4;
+    size_t smem = (size_t)2 * npad * 8 + 624 * 4 + (p->lpc.obj_dense ? 32 * 32 * 8 : 0);
     if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: n too large for the separable kernel");
     QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_lpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {

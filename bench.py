@@ -218,7 +218,8 @@ def run_own(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    step_ms, sdr_ms, cd_ms = [], [], []
+    step_ms, sdr_ms, cd_ms, cd_parts = [], [], [], []
+    part_buf = (C.c_double * 4)(); part_cnt = C.c_int32(0)
     barrier()
     wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -230,6 +231,9 @@ def run_own(args):
             global_best(b, f, seed0 - 1000 + i, device=dev)
         torch.cuda.synchronize()
         step_ms.append(ev[0].elapsed_time(ev[3])); sdr_ms.append(ev[0].elapsed_time(ev[1])); cd_ms.append(ev[1].elapsed_time(ev[2]))
+        _lib.check(L.qcqp_cd_get_timing(pack.handle, part_buf, C.byref(part_cnt)))
+        if part_cnt.value == 4:
+            cd_parts.append([part_buf[i] for i in range(4)])
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -242,10 +246,14 @@ def run_own(args):
     alg_bytes = sweeps_p1 * info.bytes_per_sweep_phase1 + sweeps_p2 * info.bytes_per_sweep_phase2
     t_step = float(np.mean(step_ms)) * 1e-3
     t_cd = float(np.mean(cd_ms)) * 1e-3
+    parts = np.mean(np.array(cd_parts), axis=0) if cd_parts else None       # [phase-1 kernel, G GEMM, phase-2 kernel, eval] ms
+    # the dominant kernel: phase 2 (cd_lpc_kernel stage 2) when the launch sequence is split, else the whole CD launch
+    t_dom = float(parts[2]) * 1e-3 if parts is not None else t_cd
+    dom_bytes = sweeps_p2 * info.bytes_per_sweep_phase2 if parts is not None else alg_bytes
     if world > 1:
-        tt = torch.tensor([t_step, t_cd], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t_step, t_cd, t_dom], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)            # device-timed, max over ranks
-        t_step, t_cd = float(tt[0].item()), float(tt[1].item())
+        t_step, t_cd, t_dom = float(tt[0].item()), float(tt[1].item()), float(tt[2].item())
         ts = torch.tensor([sweeps], dtype=torch.float64, device=dev)
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
         total_sweeps = float(ts.item())
@@ -288,9 +296,9 @@ def run_own(args):
     if rank == 0:
         peaks, peak_src = measured_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_bytes / t_cd / 1e9
+        achieved = dom_bytes / t_dom / 1e9
         traffic = None
-        kname = "qcqp::cd_lpc_kernel" if info.separable else "qcqp::cd_kernel"
+        kname = "qcqp::cd_lpc_kernel (stage 2: phase 2)" if parts is not None else ("qcqp::cd_lpc_kernel" if info.separable else "qcqp::cd_kernel")
         tpath = os.path.join(ROOT, "profiles", "cd_traffic.json")
         if os.path.exists(tpath):
             try:
@@ -324,7 +332,10 @@ def run_own(args):
                        "sweeps_per_step": {"phase1": sweeps_p1, "phase2": sweeps_p2,
                                            "phase2_max_per_restart": int(st["w2"].max()), "phase2_mean_per_restart": float(st["w2"].mean()),
                                            "phase1_steps_fast_forwarded": int(st["skip"].sum())},
-                       "kernel_ms": {"sdr_sample_eval": float(np.mean(sdr_ms)), "cd_improve": float(np.mean(cd_ms))},
+                       "kernel_ms": {"sdr_sample_eval": float(np.mean(sdr_ms)), "cd_improve": float(np.mean(cd_ms)),
+                                     "cd_parts": None if parts is None else {"phase1_kernel": float(parts[0]), "gemm_G_eq_X_P0": float(parts[1]),
+                                                                             "phase2_kernel": float(parts[2]), "batched_eval": float(parts[3])}},
+                       "cd_sequence_model_GBps": alg_bytes / t_cd / 1e9,
                        "device_vs_host_api_agree": agree, "wall_s_timed_loop": wall},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": kname, "peak_source": peak_src,
@@ -335,7 +346,8 @@ def run_own(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_sweeps / e2e_time, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_time},
-            "gpu_launches": 3 * args.steps,
+            # per step: SDR (GEMM, GEMM row-dot, finish) + CD (phase-1 kernel, GEMM, phase-2 kernel, GEMM row-dot, finish) + best
+            "gpu_launches": (9 if parts is not None else 5) * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line))

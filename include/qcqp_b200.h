@@ -162,6 +162,11 @@ int qcqp_cd_improve_device(qcqp_pack* pack, const qcqp_cd_params* params, const 
                            qcqp_rng_state* drng, double* dX, double* df0, double* dmaxviol, qcqp_cd_stats* dstats,
                            void* stream);
 
+/* Device time (ms, CUDA events on the launching stream) of the launches behind the last qcqp_cd_improve* call:
+ * ms[0] phase-1 kernel, ms[1] G = X P0 GEMM, ms[2] phase-2 kernel, ms[3] batched (f0, maxviol).  *count = 4 when the call took
+ * the separable dense-objective path (the only one split into launches), else 0.  Call after synchronising the stream. */
+int qcqp_cd_get_timing(qcqp_pack* pack, double* ms /*[4]*/, int32_t* count);
+
 /* ---- consensus ADMM: improve_admm(x0, prob, rho=...) for K rho values x R starts
  *      (qcqp.py:254-285 -> admm_phase1 :195-212, admm_phase2 :215-251, onecons_qcqp utilities.py:149-196,
  *       QCQPForm.better :135-146).

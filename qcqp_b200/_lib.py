@@ -66,6 +66,7 @@ EXPORTS = {
                                   C.c_void_p, C.c_void_p]),
     "qcqp_cd_improve_device": (C.c_int, [C.c_void_p, C.POINTER(CdParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcqp_cd_get_timing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qcqp_admm_pack_eig": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qcqp_admm_improve": (C.c_int, [C.c_void_p, C.POINTER(AdmmParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

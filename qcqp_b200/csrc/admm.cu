@@ -17,7 +17,7 @@ struct AdmmK {
     int phase1;
 };
 
-constexpr int ADMM_THREADS = 256;
+constexpr int ADMM_THREADS = 512;   // 16 warps: 16 projections in flight per run; 128 registers each fill the file
 constexpr int ADMM_WARPS = ADMM_THREADS / 32;
 
 struct AdmmSmem {

@@ -119,6 +119,24 @@ extern "C" int qcqp_cd_improve(qcqp_pack* pack, const qcqp_cd_params* params, co
     return QCQP_OK;
 }
 
+// Device time of the launches behind the last qcqp_cd_improve(_device) call on this pack, from CUDA events recorded on the
+// launching stream: ms[0] phase-1 kernel, ms[1] G = X P0 GEMM, ms[2] phase-2 kernel, ms[3] batched (f0, maxviol).
+// Only the separable dense-objective path is split into launches; otherwise *count is 0.  Call after synchronising.
+extern "C" int qcqp_cd_get_timing(qcqp_pack* pack, double* ms, int32_t* count)
+{
+    TRY(check_pack(pack, "qcqp_cd_get_timing"));
+    if (!ms || !count) return fail(QCQP_ERR_INVALID, "qcqp_cd_get_timing: null argument");
+    *count = 0;
+    if (!pack->ev_ok || pack->ev_count < 5) return QCQP_OK;
+    for (int i = 0; i < 4; i++) {
+        float t = 0.f;
+        QCQP_CUDA_TRY(cudaEventElapsedTime(&t, pack->ev[i], pack->ev[i + 1]));
+        ms[i] = (double)t;
+    }
+    *count = 4;
+    return QCQP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int qcqp_admm_improve_device(qcqp_pack* pack, const qcqp_admm_params* params, const double* drhos, const double* dZinv,
                                         int32_t K, const double* dX0, int32_t R, double* dX, double* df0, double* dmaxviol,

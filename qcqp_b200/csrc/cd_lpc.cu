@@ -606,13 +606,26 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
         if (rc != QCQP_OK) return rc;
         double* G = (double*)p->ws;
         qcqp_cd_stats* stats = dstats ? dstats : (qcqp_cd_stats*)((char*)p->ws + gbytes);
+        if (!p->ev_ok) {
+            for (int i = 0; i < 6; i++) QCQP_CUDA_TRY(cudaEventCreate(&p->ev[i]));
+            p->ev_ok = true;
+        }
+        p->ev_count = 0;
+        QCQP_CUDA_TRY(cudaEventRecord(p->ev[0], stream));
         cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 1, dX0, R, drng, dX, nullptr, df0, dmv, stats);
         QCQP_CUDA_TRY(cudaGetLastError());
+        QCQP_CUDA_TRY(cudaEventRecord(p->ev[1], stream));
         rc = gemm_plain_launch(R, n, n, dX, n, p->v.dense_P, p->v.ld, G, npad, stream);
         if (rc != QCQP_OK) return rc;
+        QCQP_CUDA_TRY(cudaEventRecord(p->ev[2], stream));
         cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 2, dX0, R, drng, dX, G, df0, dmv, stats);
         QCQP_CUDA_TRY(cudaGetLastError());
-        return eval_launch(p, dX, R, df0, dmv, nullptr, stream);
+        QCQP_CUDA_TRY(cudaEventRecord(p->ev[3], stream));
+        rc = eval_launch(p, dX, R, df0, dmv, nullptr, stream);
+        if (rc != QCQP_OK) return rc;
+        QCQP_CUDA_TRY(cudaEventRecord(p->ev[4], stream));
+        p->ev_count = 5;
+        return QCQP_OK;
     }
     cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 0, dX0, R, drng, dX, nullptr, df0, dmv, dstats);
     QCQP_CUDA_TRY(cudaGetLastError());

@@ -112,6 +112,10 @@ struct qcqp_pack {
     int objective_dense;
     bool lpc_ok;
     qcqp::LpcView lpc;
+    // CUDA events around the launches of the last qcqp_cd_improve* call (see qcqp_cd_get_timing)
+    cudaEvent_t ev[6];
+    bool ev_ok;
+    int ev_count;
 };
 
 namespace qcqp {

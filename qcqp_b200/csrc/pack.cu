@@ -108,6 +108,7 @@ extern "C" void qcqp_pack_destroy(qcqp_pack* p)
     if (p->ws) cudaFree(p->ws);
     if (p->io) cudaFree(p->io);
     if (p->ws2) cudaFree(p->ws2);
+    if (p->ev_ok) for (int i = 0; i < 6; i++) cudaEventDestroy(p->ev[i]);
     delete p;
 }
 
@@ -267,6 +268,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     std::memset(&p->v, 0, sizeof(p->v));
     std::memset(&p->info, 0, sizeof(p->info));
     p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->ws2 = nullptr; p->ws2_bytes = 0; p->has_eig = false; p->lpc_ok = false;
+    p->ev_ok = false; p->ev_count = 0;
     std::memset(&p->lpc, 0, sizeof(p->lpc));
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;

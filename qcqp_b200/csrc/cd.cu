@@ -20,7 +20,6 @@
 namespace qcqp {
 
 constexpr int CD_LONG_ROW = 48;      // sparse rows longer than this are dotted by the whole warp (fast mode)
-constexpr int CD_SMALL_EVENTS = 40;  // up to this many events lane 0 insertion-sorts; beyond, warp bitonic sort
 
 struct CdLayout {
     int W;            // restart warps per CTA
@@ -28,10 +27,10 @@ struct CdLayout {
     int sc_cap;       // coefficient scratch entries in smem (0: global scratch)
     int fval_smem;    // cached f_j in smem?
     int grad;         // cached dense row dots g_d = P_d x in smem (gradient mode)
-    int evN;          // event capacity (power of two)
+    int hcap;         // hole capacity (power of two, >= 32)
     // byte offsets inside the dynamic smem block
     unsigned off_bar, off_ring, off_warp0, warp_stride;
-    unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_evk, o_evd, o_clo, o_chi, o_dd, o_misc, o_g;
+    unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_hx, o_clo, o_chi, o_dd, o_misc, o_g;
     unsigned total;
 };
 
@@ -41,12 +40,11 @@ struct WarpMem {
     double* x;
     double* fval;
     uint32_t* mt;
-    double* scp; double* scq; double* scr; int* screl;
-    double* evk; int* evd;
+    double2* hx;      // holes (a, b) of the two-interval constraints of this step
     double* clo; double* chi;
     double* dd;       // dots of the dense rows of this step, by dense slot
     double* g;        // gradient mode: g[d][npad] = P_d x for every dense slot
-    int* misc;        // [0] event counter
+    int* misc;
 };
 
 enum { PH_P1 = 0, PH_P2 = 1, PH_DONE = 2 };
@@ -88,57 +86,136 @@ __device__ __forceinline__ double dense_row_dot_seq(const double* row, const dou
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// warp-wide bitonic sort of (key, delta) pairs in shared memory; N is a power of two
+// Sweep line, GPU formulation (onevar.cuh "HOLE formulation" has the argument and the scalar statement that the CPU
+// tests hold against the reference): singles and hulls are folded into (L, H, mu); only the holes of two-interval
+// constraints are sorted -- by their start, 16-byte (a, b) records -- and one prefix-max scan of their ends yields
+// the feasible pieces in ascending order.  <= 32 holes: registers + shuffles; more: shared memory.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bitonic_sort_events(double* key, int* del, int N, int lane)
+__device__ __forceinline__ void bitonic_sort_holes_smem(double2* h, int N, int lane)
 {
     for (int k = 2; k <= N; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < N; i += 32) {
-                int p = i ^ j;
-                if (p > i) {
-                    double a = key[i], b = key[p];
-                    bool up = ((i & k) == 0);
-                    if ((a > b) == up && a != b) {
-                        key[i] = b; key[p] = a;
-                        int t = del[i]; del[i] = del[p]; del[p] = t;
-                    }
-                }
+#pragma unroll 4
+            for (int t = lane; t < (N >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const double2 a = h[i], b = h[p];
+                const bool up = ((i & k) == 0);
+                if ((a.x > b.x) == up && a.x != b.x) { h[i] = b; h[p] = a; }
             }
             __syncwarp();
         }
     }
 }
-
-// ---------------------------------------------------------------------------------------------------------
-// tail of onevar_qcqp once the explicit (two-interval) events sit in w.evk/w.evd[0..nev): sentinels + fold, sort,
-// sweep line, minimiser.  Lane 0 owns the RNG.  Returns found (warp-uniform); xout/err valid in every lane.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int solve_tail_sorted(const WarpMem& w, const Fold& f, int nev, double p0, double q0, double r0, MtRng& rng,
-                                                 int lane, double* xout, int* err)
+__device__ __forceinline__ void bitonic_sort_holes_reg(double& a, double& b, int lane)
 {
-    int found = 0, e = 0;
-    double xv = 0.0;
-    if (nev + 4 <= CD_SMALL_EVENTS) {
-        if (lane == 0) {
-            nev = finish_events(f, w.evk, w.evd, nev);
-            insertion_sort_events(w.evk, w.evd, nev);
-            int nC = sweep_sorted(w.evk, w.evd, nev, f.mcnt, w.clo, w.chi);
-            found = choose_point(p0, q0, r0, w.clo, w.chi, nC, rng, &xv, &e);
-        }
-    } else {
-        if (lane == 0) nev = finish_events(f, w.evk, w.evd, nev);
-        nev = bcast_i(nev, 0);
-        int N2 = 1;
-        while (N2 < nev) N2 <<= 1;
-        for (int i = nev + lane; i < N2; i += 32) { w.evk[i] = QCQP_INF; w.evd[i] = 0; }   // joins the +inf sentinel, adds 0
-        __syncwarp();
-        bitonic_sort_events(w.evk, w.evd, N2, lane);
-        if (lane == 0) {
-            int nC = sweep_sorted(w.evk, w.evd, N2, f.mcnt, w.clo, w.chi);
-            found = choose_point(p0, q0, r0, w.clo, w.chi, nC, rng, &xv, &e);
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const double pa = __shfl_xor_sync(FULL, a, j), pb = __shfl_xor_sync(FULL, b, j);
+            const bool keepmin = (((lane & j) == 0) == ((lane & k) == 0));
+            const bool swap = keepmin ? (pa < a) : (pa > a);
+            if (swap) { a = pa; b = pb; }
         }
     }
+}
+
+struct HoleScan {
+    double carryM;    // max(L, ends of the holes of earlier chunks)          (warp-uniform)
+    double prevA;     // start of the last hole of the previous chunk         (warp-uniform)
+    bool havePrev;
+    bool blocked;     // per lane: one of my holes has a <= H <= b
+    double stH;       // per lane: max{b : b < H} over my holes
+    int nC;           // pieces written so far                                (warp-uniform)
+};
+
+// one chunk of 32 holes in ascending order of a (lane = position); nextA = start of the first hole of the next chunk
+__device__ __forceinline__ void scan_hole_chunk(const WarpMem& w, const Fold& f, double a, double b, double nextA, HoleScan& hs, int lane)
+{
+    double inc = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o && t > inc) inc = t;
+    }
+    const double exc = __shfl_up_sync(FULL, inc, 1);
+    double M = hs.carryM;
+    if (lane > 0 && exc > M) M = exc;
+    const double ap = __shfl_up_sync(FULL, a, 1);
+    const bool tiep = (lane > 0) ? (ap == a) : (hs.havePrev && hs.prevA == a);
+    double an = __shfl_down_sync(FULL, a, 1);
+    if (lane == 31) an = nextA;
+    const bool valid = !tiep && (an != a) && (M < a) && (a < f.H);
+    const unsigned vb = __ballot_sync(FULL, valid);
+    if (valid) {
+        const int pos = hs.nC + __popc(vb & ((1u << lane) - 1u));
+        w.clo[pos] = M; w.chi[pos] = a;
+    }
+    hs.nC += __popc(vb);
+    if (a <= f.H && f.H <= b) hs.blocked = true;
+    if (b < f.H && b > hs.stH) hs.stH = b;
+    const double tot = __shfl_sync(FULL, inc, 31);
+    if (tot > hs.carryM) hs.carryM = tot;
+    hs.prevA = __shfl_sync(FULL, a, 31);
+    hs.havePrev = true;
+}
+
+// tail of onevar_qcqp: f = the all-reduced fold (singles + hulls), nh holes -- in (ra, rb), one per lane, when
+// in_regs, else in w.hx[0..nh).  Lane 0 owns the RNG.  Returns found (warp-uniform); xout/err valid in every lane.
+__device__ __forceinline__ int holes_finish(const WarpMem& w, const Fold& f, int nh, bool in_regs, double ra, double rb, double p0, double q0,
+                                            double r0, MtRng& rng, int lane, double* xout, int* err)
+{
+    *xout = 0.0;
+    *err = 0;
+    int nC = 0;
+    if (f.mcnt == 0) {
+        if (lane == 0) { w.clo[0] = -QCQP_INF; w.chi[0] = QCQP_INF; }   // only the sentinel pair: all of R
+        nC = 1;
+    } else {
+        if (f.nempty > 0 || !(f.L < f.H)) return 0;   // the running total never gets full
+        HoleScan hs;
+        hs.carryM = f.L; hs.prevA = 0.0; hs.havePrev = false; hs.blocked = false; hs.stH = -QCQP_INF; hs.nC = 0;
+        if (nh > 0) {
+            if (in_regs || nh <= 32) {
+                double a = ra, b = rb;
+                if (!in_regs) {
+                    a = QCQP_INF; b = QCQP_INF;
+                    if (lane < nh) { const double2 t = w.hx[lane]; a = t.x; b = t.y; }
+                }
+                bitonic_sort_holes_reg(a, b, lane);
+                scan_hole_chunk(w, f, a, b, QCQP_INF, hs, lane);
+            } else {
+                int N2 = 64;
+                while (N2 < nh) N2 <<= 1;
+                for (int i = nh + lane; i < N2; i += 32) w.hx[i] = make_double2(QCQP_INF, QCQP_INF);   // pads are inert
+                __syncwarp();
+                bitonic_sort_holes_smem(w.hx, N2, lane);
+                const int nchunk = (nh + 31) >> 5;
+                double2 cur = w.hx[lane];
+                for (int c = 0; c < nchunk; c++) {
+                    const double2 nxt = w.hx[(c + 1 < (N2 >> 5)) ? ((c + 1) << 5) + lane : lane];
+                    const double nextA = (c + 1 < (N2 >> 5)) ? __shfl_sync(FULL, nxt.x, 0) : QCQP_INF;
+                    scan_hole_chunk(w, f, cur.x, cur.y, nextA, hs, lane);
+                    cur = nxt;
+                }
+            }
+        }
+        nC = hs.nC;
+        if (f.mu == 1 && f.H < QCQP_INF) {
+            const bool blocked = __any_sync(FULL, hs.blocked);
+            double st = warp_max(hs.stH);
+            if (f.L > st) st = f.L;
+            if (!blocked) {
+                if (lane == 0) { w.clo[nC] = st; w.chi[nC] = f.H; }
+                nC++;
+            }
+        }
+    }
+    __syncwarp();
+    int found = 0, e = 0;
+    double xv = 0.0;
+    if (lane == 0) found = choose_point(p0, q0, r0, w.clo, w.chi, nC, rng, &xv, &e);
     __syncwarp();
     *xout = bcast(xv, 0);
     *err = bcast_i(e, 0);
@@ -164,35 +241,49 @@ __device__ __forceinline__ void fold_bcast(Fold& f, int src)
 // ---------------------------------------------------------------------------------------------------------
 // onevar_qcqp, general path: the mk constraint coefficients are in scratch (any mk).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int solve_level(const WarpMem& w, int mk, double s, double p0, double q0, double r0, MtRng& rng,
+struct Scratch {
+    double* p; double* q; double* r; int* rel;
+};
+
+__device__ __forceinline__ int solve_level(const WarpMem& w, const Scratch& sc, int mk, double s, double p0, double q0, double r0, MtRng& rng,
                                            int lane, double* xout, int* err)
 {
     *err = 0;
     *xout = 0.0;
     Fold f;
     f.init();
-    if (lane == 0) w.misc[0] = 0;
-    __syncwarp();
-    for (int i = lane; i < mk; i += 32) {
-        double p = w.scp[i], q = w.scq[i];
-        if (p == 0.0 && q == 0.0) continue;   // nfs filter of qcqp.py:116,166
-        f.mcnt++;
-        Ival I[2];
-        int c = feasible_intervals(p, q, w.scr[i], w.screl[i], s, I);
-        if (c == 0) f.nempty++;
-        else if (c == 1) f.add_single(I[0].lo, I[0].hi);
-        else {
-            int at = atomicAdd(&w.misc[0], 4);
-            w.evk[at] = I[0].lo; w.evd[at] = +1;
-            w.evk[at + 1] = I[0].hi; w.evd[at + 1] = -1;
-            w.evk[at + 2] = I[1].lo; w.evd[at + 2] = +1;
-            w.evk[at + 3] = I[1].hi; w.evd[at + 3] = -1;
+    int nh = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < mk; base += 32) {
+        const int i = base + lane;
+        bool hole = false;
+        Hole hh;
+        hh.a = hh.b = 0.0;
+        if (i < mk) {
+            const double p = sc.p[i], q = sc.q[i];
+            if (!(p == 0.0 && q == 0.0)) {   // nfs filter of qcqp.py:116,166
+                Ival I[2];
+                const int c = feasible_intervals(p, q, sc.r[i], sc.rel[i], s, I);
+                hole = fold_constraint(f, c, I, &hh);
+            }
+        }
+        // some constraint has no feasible point at this level: the total never reaches m + 1
+        if (__any_sync(FULL, f.nempty > 0)) return 0;
+        const unsigned hb = __ballot_sync(FULL, hole);
+        if (hb) {
+            if (hole) w.hx[nh + __popc(hb & lt)] = make_double2(hh.a, hh.b);
+            nh += __popc(hb);
+        }
+        // long lists (circle packing's r: one interval from each of 20 701 constraints): once the partial intersection of the
+        // singles is empty the final one is too
+        if ((base & 511) == 480 && base + 32 < mk) {
+            const double Lp = warp_max(f.L), Hp = -warp_max(-f.H);
+            if (!(Lp < Hp)) return 0;
         }
     }
     fold_allreduce(f);
     __syncwarp();
-    if (f.nempty > 0) return 0;   // some constraint has no feasible point at this level: the total never reaches m + 1
-    return solve_tail_sorted(w, f, w.misc[0], p0, q0, r0, rng, lane, xout, err);
+    return holes_finish(w, f, nh, false, 0.0, 0.0, p0, q0, r0, rng, lane, xout, err);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -238,6 +329,17 @@ __device__ __forceinline__ int solve_small(const WarpMem& w, bool active, double
     const unsigned act = __ballot_sync(FULL, counted);
     const unsigned two = __ballot_sync(FULL, counted && c == 2);
     const int nact = __popc(act);
+    if (__popc(two) >= 2) {
+        // several two-interval constraints: hull into the fold, hole (if any) stays in this lane's registers
+        pc.valid = false;
+        double ha = QCQP_INF, hb = QCQP_INF;
+        if (counted && c == 2) {
+            f.add_single(I[0].lo, I[1].hi);
+            if (I[0].hi < I[1].lo) { ha = I[0].hi; hb = I[1].lo; }
+        }
+        fold_allreduce(f);
+        return holes_finish(w, f, 32, true, ha, hb, p0, q0, r0, rng, lane, xout, err);
+    }
     const int only = __ffs(act) - 1;
     // a single counted constraint whose feasible set is memoised: the pieces of the previous call are still in place
     const bool reuse = (nact == 1) && pc.valid && pc.src == only && (__ballot_sync(FULL, hit) & act) != 0;
@@ -268,16 +370,7 @@ __device__ __forceinline__ int solve_small(const WarpMem& w, bool active, double
         *err = bcast_i(e, 0);
         return bcast_i(found, 0);
     }
-    pc.valid = false;
-    if (counted && c == 2) {
-        const int at = 4 * __popc(two & ((1u << lane) - 1u));
-        w.evk[at] = I[0].lo; w.evd[at] = +1;
-        w.evk[at + 1] = I[0].hi; w.evd[at + 1] = -1;
-        w.evk[at + 2] = I[1].lo; w.evd[at + 2] = +1;
-        w.evk[at + 3] = I[1].hi; w.evd[at + 3] = -1;
-    }
-    __syncwarp();
-    return solve_tail_sorted(w, f, 4 * ntwo, p0, q0, r0, rng, lane, xout, err);
+    return 0;   // not reached: ntwo >= 2 is handled above
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -518,8 +611,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
     WarpMem w;
     w.x = reinterpret_cast<double*>(wb + lay.o_x);
     w.mt = reinterpret_cast<uint32_t*>(wb + lay.o_mt);
-    w.evk = reinterpret_cast<double*>(wb + lay.o_evk);
-    w.evd = reinterpret_cast<int*>(wb + lay.o_evd);
+    w.hx = reinterpret_cast<double2*>(wb + lay.o_hx);
     w.clo = reinterpret_cast<double*>(wb + lay.o_clo);
     w.chi = reinterpret_cast<double*>(wb + lay.o_chi);
     w.dd = reinterpret_cast<double*>(wb + lay.o_dd);
@@ -527,16 +619,18 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
     w.g = reinterpret_cast<double*>(wb + lay.o_g);
     const size_t rr = live ? (size_t)restart : 0;
     w.fval = lay.fval_smem ? reinterpret_cast<double*>(wb + lay.o_fval) : ws_fval + rr * (size_t)(m + 1);
-    if (lay.sc_cap > 0) {
-        w.scp = reinterpret_cast<double*>(wb + lay.o_scp);
-        w.scq = reinterpret_cast<double*>(wb + lay.o_scq);
-        w.scr = reinterpret_cast<double*>(wb + lay.o_scr);
-        w.screl = reinterpret_cast<int*>(wb + lay.o_screl);
-    } else {
-        w.scp = ws_scr + rr * 3 * (size_t)P.max_inc;
-        w.scq = w.scp + P.max_inc;
-        w.scr = w.scq + P.max_inc;
-        w.screl = ws_screl + rr * (size_t)P.max_inc;
+    // coefficient scratch: shared memory for coordinates with <= sc_cap incident forms, a per-restart HBM block beyond
+    Scratch sc_s, sc_g;
+    sc_s.p = reinterpret_cast<double*>(wb + lay.o_scp);
+    sc_s.q = reinterpret_cast<double*>(wb + lay.o_scq);
+    sc_s.r = reinterpret_cast<double*>(wb + lay.o_scr);
+    sc_s.rel = reinterpret_cast<int*>(wb + lay.o_screl);
+    sc_g = sc_s;
+    if (P.max_inc > lay.sc_cap) {
+        sc_g.p = ws_scr + rr * 3 * (size_t)P.max_inc;
+        sc_g.q = sc_g.p + P.max_inc;
+        sc_g.r = sc_g.q + P.max_inc;
+        sc_g.rel = ws_screl + rr * (size_t)P.max_inc;
     }
 
     MtRng rng;
@@ -743,6 +837,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
             const bool obj_inc = __ballot_sync(FULL, has_obj) != 0;
             const int cbeg = beg + (obj_inc ? 1 : 0);
             const int mk = end - cbeg;
+            const Scratch sc = (mk <= lay.sc_cap) ? sc_s : sc_g;
             double p0 = 0.0, q0 = 0.0, r0 = 0.0;
             if (phase == PH_P2) {
                 r0 = w.fval[0];
@@ -778,10 +873,10 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                 if (mine) {
                     const int j = (int)(mt.fw & INC_FORM_MASK);
                     const double t1 = 2 * dot + mt.qk;
-                    w.scp[i] = mt.t2;
-                    w.scq[i] = t1;
-                    w.scr[i] = w.fval[j] - xk * (mt.t2 * xk + t1);
-                    w.screl[i] = (int)((mt.fw >> INC_RELOP_SHIFT) & 3);
+                    sc.p[i] = mt.t2;
+                    sc.q[i] = t1;
+                    sc.r[i] = w.fval[j] - xk * (mt.t2 * xk + t1);
+                    sc.rel[i] = (int)((mt.fw >> INC_RELOP_SHIFT) & 3);
                 }
             }
             __syncwarp();
@@ -790,10 +885,10 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                 double vmax = -QCQP_INF;
                 int cz = 0;
                 for (int i = lane; i < mk; i += 32) {
-                    double p = w.scp[i], q = w.scq[i];
+                    double p = sc.p[i], q = sc.q[i];
                     if (p == 0.0 && q == 0.0) continue;
                     cz++;
-                    double v = violation_of(w.screl[i], onevar_eval(p, q, w.scr[i], xk));
+                    double v = violation_of(sc.rel[i], onevar_eval(p, q, sc.r[i], xk));
                     vmax = (v > vmax) ? v : vmax;
                 }
                 cz = warp_sum_i(cz);
@@ -806,7 +901,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                         const double s = (ss + es) / 2;
                         double xi;
                         int err;
-                        int ok = solve_level(w, mk, s, 0.0, 0.0, 0.0, rng, lane, &xi, &err);
+                        int ok = solve_level(w, sc, mk, s, 0.0, 0.0, 0.0, rng, lane, &xi, &err);
                         if (err) { st.status = err; dead = true; break; }
                         if (!ok) ss = s;
                         else { new_xi = xi; new_viol = s; es = s; }
@@ -823,7 +918,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                 st.steps_p2++;
                 double xi;
                 int err;
-                int ok = solve_level(w, mk, viol_p2, p0, q0, r0, rng, lane, &xi, &err);
+                int ok = solve_level(w, sc, mk, viol_p2, p0, q0, r0, rng, lane, &xi, &err);
                 if (err) { st.status = err; dead = true; }
                 else if (ok && fabs(xi - xk) > tol) { move = true; new_xi = xi; update_counter = 0; st.updates_p2++; }
                 else {
@@ -835,7 +930,7 @@ __global__ void __launch_bounds__(256, 1) cd_kernel(PackView P, CdK prm, CdLayou
                 const double b = new_xi;
                 for (int i = lane; i < mk; i += 32) {
                     int j = (int)(P.inc_form[cbeg + i] & INC_FORM_MASK);
-                    w.fval[j] = w.scr[i] + b * (w.scp[i] * b + w.scq[i]);
+                    w.fval[j] = sc.r[i] + b * (sc.p[i] * b + sc.q[i]);
                 }
                 if (lane == 0 && phase != PH_P1 && obj_inc) w.fval[0] = r0 + b * (p0 * b + q0);
             }
@@ -891,10 +986,12 @@ static int plan_layout(const qcqp_pack* p, int R, bool want_grad, CdLayout* L)
     const int sms = num_sms(p->device);
     CdLayout l;
     memset(&l, 0, sizeof(l));
-    int evN = 8;
-    while (evN < v.ev_cap) evN <<= 1;
-    l.evN = evN;
-    l.sc_cap = (v.max_inc <= 1024) ? (v.max_inc > 0 ? v.max_inc : 1) : 0;
+    int hcap = 32;
+    while (hcap < v.max_two) hcap <<= 1;
+    l.hcap = hcap;
+    // coefficient scratch in shared memory for every coordinate with <= 1024 incident forms; a coordinate beyond that
+    // (circle packing's r: 20 702) uses the per-restart HBM block
+    l.sc_cap = (v.max_inc <= 1024) ? (v.max_inc > 0 ? v.max_inc : 1) : (v.max_inc_small > 0 ? v.max_inc_small : 1);
     l.fval_smem = ((size_t)(v.m + 1) * 8 <= 24 * 1024) ? 1 : 0;
     unsigned o = 0;
     l.o_x = o; o += align_up((unsigned)v.n * 8, 16);
@@ -904,10 +1001,9 @@ static int plan_layout(const qcqp_pack* p, int R, bool want_grad, CdLayout* L)
     l.o_scq = o; o += align_up((unsigned)l.sc_cap * 8, 16);
     l.o_scr = o; o += align_up((unsigned)l.sc_cap * 8, 16);
     l.o_screl = o; o += align_up((unsigned)l.sc_cap * 4, 16);
-    l.o_evk = o; o += (unsigned)evN * 8;
-    l.o_evd = o; o += (unsigned)evN * 4;
-    l.o_clo = o; o += align_up((unsigned)(evN / 2 + 2) * 8, 16);
-    l.o_chi = o; o += align_up((unsigned)(evN / 2 + 2) * 8, 16);
+    l.o_hx = o; o += (unsigned)hcap * 16;
+    l.o_clo = o; o += align_up((unsigned)(hcap + 2) * 8, 16);
+    l.o_chi = o; o += align_up((unsigned)(hcap + 2) * 8, 16);
     l.o_dd = o; o += align_up((unsigned)(v.n_dense > 0 ? v.n_dense : 1) * 8, 16);
     l.o_misc = o; o += 16;
     l.o_g = o;
@@ -969,8 +1065,8 @@ int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R,
     if (rc != QCQP_OK) return rc;
     const PackView& v = p->v;
     size_t fval_bytes = L.fval_smem ? 0 : (size_t)R * (v.m + 1) * 8;
-    size_t scr_bytes = L.sc_cap > 0 ? 0 : (size_t)R * 3 * v.max_inc * 8;
-    size_t rel_bytes = L.sc_cap > 0 ? 0 : (size_t)R * v.max_inc * 4;
+    size_t scr_bytes = (v.max_inc <= L.sc_cap) ? 0 : (size_t)R * 3 * v.max_inc * 8;
+    size_t rel_bytes = (v.max_inc <= L.sc_cap) ? 0 : (size_t)R * v.max_inc * 4;
     size_t a1 = (fval_bytes + 255) & ~(size_t)255, a2 = (scr_bytes + 255) & ~(size_t)255;
     rc = ensure_workspace(p, a1 + a2 + rel_bytes + 256);
     if (rc != QCQP_OK) return rc;

@@ -45,7 +45,8 @@ constexpr uint32_t INC_DENSE_BIT = 0x80000000u;
 struct PackView {
     int n, m, n_dense, ld;
     int max_inc;     // max incidences of one coordinate
-    int ev_cap;      // event slots the 1-D sweep-line can need (4 per two-interval-capable incidence + 4)
+    int max_inc_small;   // max incidences over the coordinates that have at most 1024 (their coefficient scratch lives in shared memory)
+    int max_two;     // max number of two-interval-capable incidences of one coordinate (holes the 1-D sweep line can need)
     const int* inc_ptr;
     const uint32_t* inc_form;
     const double* inc_t2;

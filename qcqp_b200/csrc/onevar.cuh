@@ -293,6 +293,62 @@ QCQP_HD int sweep_small8(const Fold& f, bool has_two, const Ival& I0, const Ival
 #undef QCQP_CSWAP
 
 // ---------------------------------------------------------------------------------------------------------
+// HOLE formulation of the sweep line (what cd.cu's warp-parallel solver implements; this scalar statement of it is
+// what tests/test_onevar_host.py checks against the reference's dict/sorted sweep, ties and quirks included).
+//
+// A two-interval feasible set [a0,b0] u [a1,b1] is its hull [a0,b1] -- folded like any single interval -- minus the
+// open hole (b0,a1).  The hole adds +1 at -inf and -1 at +inf, i.e. one more always-covering constraint, so the
+// events at every finite key are those of the reference.  A zero-width hole nets 0 at its key and is dropped, as the
+// reference drops zero-net dict entries.  With L = max lo, H = min hi (multiplicity mu) over the singles and hulls, the
+// reference reports a piece ending at key e iff the running total is full just before e and the net count at e is -1:
+//   * e = a_i, a hole start:  no other hole starts at e,  max(L, max{b_j : a_j < e}) < e < H;
+//   * e = H (finite):         mu == 1, L < H, no hole with a_j <= H <= b_j;
+// and the piece starts at the previous nonzero-net key, which is max(L, max{b_j : b_j < e}).  Pieces come out in
+// ascending order of e (the H piece last).  No sorting of the 4-per-constraint events is needed: only of the holes.
+// ---------------------------------------------------------------------------------------------------------
+struct Hole { double a, b; };
+
+// appends constraint i's feasible set (c intervals from feasible_intervals) to the fold / hole list
+QCQP_HD bool fold_constraint(Fold& f, int c, const Ival* I, Hole* hole)
+{
+    f.mcnt++;
+    if (c == 0) { f.nempty++; return false; }
+    if (c == 1) { f.add_single(I[0].lo, I[0].hi); return false; }
+    f.add_single(I[0].lo, I[1].hi);
+    if (I[0].hi < I[1].lo) { hole->a = I[0].hi; hole->b = I[1].lo; return true; }
+    return false;
+}
+
+QCQP_HD int pieces_from_holes(const Fold& f, Hole* h, int nh, double* c_lo, double* c_hi)
+{
+    if (f.mcnt == 0) { c_lo[0] = -QCQP_INF; c_hi[0] = QCQP_INF; return 1; }   // only the sentinel pair: one piece, all of R
+    for (int i = 1; i < nh; i++) {      // sort the holes by their start
+        Hole t = h[i];
+        int j = i - 1;
+        while (j >= 0 && h[j].a > t.a) { h[j + 1] = h[j]; j--; }
+        h[j + 1] = t;
+    }
+    int nC = 0;
+    double M = f.L;                     // max(L, b_j of the holes before i)
+    for (int i = 0; i < nh; i++) {
+        const double e = h[i].a;
+        const bool tie = (i > 0 && h[i - 1].a == e) || (i + 1 < nh && h[i + 1].a == e);
+        if (!tie && M < e && e < f.H) { c_lo[nC] = M; c_hi[nC] = e; nC++; }
+        if (h[i].b > M) M = h[i].b;
+    }
+    if (f.mu == 1 && f.H < QCQP_INF && f.L < f.H) {
+        bool blocked = false;
+        double st = f.L;
+        for (int i = 0; i < nh; i++) {
+            if (h[i].a <= f.H && f.H <= h[i].b) blocked = true;
+            if (h[i].b < f.H && h[i].b > st) st = h[i].b;
+        }
+        if (!blocked) { c_lo[nC] = st; c_hi[nC] = f.H; nC++; }
+    }
+    return nC;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // the minimiser of f0 = (p, q, r) over the pieces (utilities.py:263-288).  Returns 1 and *xout, 0 for None.
 // *err: QCQP_RUN_UNBOUNDED_UNIFORM when the reference would raise OverflowError.
 // ---------------------------------------------------------------------------------------------------------

@@ -226,11 +226,13 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
                 if (d->p_col[t] != k) { row_col[w] = d->p_col[t]; row_val[w] = d->p_val[t]; w++; }
         }
 
-    // capacity of the sweep-line event list: only incidences that can yield two intervals need event slots
+    // capacity of the sweep line's hole list: only incidences that can yield two intervals need a slot
     // (get_feasible_intervals, utilities.py:198-232: p < -tol, or '==' with |p| > tol; tol = 1e-4 is fixed there)
-    int max_inc = 0, ev_cap = 8;
+    int max_inc = 0, max_inc_small = 0, max_two = 0;
     for (int k = 0; k < n; k++) {
-        max_inc = std::max(max_inc, inc_ptr[k + 1] - inc_ptr[k]);
+        const int cnt = inc_ptr[k + 1] - inc_ptr[k];
+        max_inc = std::max(max_inc, cnt);
+        if (cnt <= 1024) max_inc_small = std::max(max_inc_small, cnt);
         int two = 0;
         for (int e = inc_ptr[k]; e < inc_ptr[k + 1]; e++) {
             int rel = (inc_form[e] >> INC_RELOP_SHIFT) & 3;
@@ -238,7 +240,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
             if (rel == QCQP_RELOP_NONE) continue;
             if (t2 < -1e-4 || (rel == QCQP_RELOP_EQ && std::fabs(t2) > 1e-4)) two++;
         }
-        ev_cap = std::max(ev_cap, 4 * two + 8);
+        max_two = std::max(max_two, two);
     }
 
     // ---- form-major COO (sparse forms only) and dense matrices ----------------------------------------------
@@ -273,7 +275,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;
     PackView& v = p->v;
-    v.n = n; v.m = m; v.n_dense = nd; v.ld = ld; v.max_inc = max_inc; v.ev_cap = ev_cap;
+    v.n = n; v.m = m; v.n_dense = nd; v.ld = ld; v.max_inc = max_inc; v.max_inc_small = max_inc_small; v.max_two = max_two;
     int rc = QCQP_OK;
 #define UP(vec, field) if (rc == QCQP_OK) rc = upload(p, vec, &v.field)
     UP(inc_ptr, inc_ptr); UP(inc_form, inc_form); UP(inc_t2, inc_t2); UP(inc_qk, inc_qk);

@@ -54,23 +54,24 @@ def test_device_intervals_match_reference(shim, golden):
 
 def test_device_solver_matches_reference_goldens(shim, golden):
     for c in golden["onevar"]:
-        st = orc.RngState.from_seed(c["seed"])
-        rc, x = _solve(shim, c["f0"], [tuple(f) for f in c["fs"]], c["s"], st)
-        if c["error"]:
-            assert rc == -2
-            continue
-        if c["result"] is None:
-            assert rc == 0, c
-        else:
-            assert rc == 1 and x == c["result"], c
-        assert st.pos == c["rng"]["pos"], c
+        for mode in (0, 1, 2):          # register path, sorted-event path, hole formulation
+            st = orc.RngState.from_seed(c["seed"])
+            rc, x = _solve(shim, c["f0"], [tuple(f) for f in c["fs"]], c["s"], st, mode)
+            if c["error"]:
+                assert rc == -2
+                continue
+            if c["result"] is None:
+                assert rc == 0, (mode, c)
+            else:
+                assert rc == 1 and x == c["result"], (mode, c)
+            assert st.pos == c["rng"]["pos"], (mode, c)
 
 
 def test_device_solver_matches_oracle_random(shim):
     """Wider net than the goldens: many constraints, duplicated constraints, shared endpoints, degenerate forms."""
     rs = np.random.RandomState(2024)
     for t in range(4000):
-        m = int(rs.randint(0, 12))
+        m = int(rs.randint(0, 12)) if t % 7 else int(rs.randint(12, 60))
         fs = []
         for _ in range(m):
             kind = rs.randint(0, 7)
@@ -96,7 +97,7 @@ def test_device_solver_matches_oracle_random(shim):
             err = False
         except OverflowError:
             err = True
-        for force_general in (0, 1):    # register path (<= 1 two-interval constraint) and the sorted-event path
+        for force_general in (0, 1, 2):    # register path (<= 1 two-interval constraint), sorted-event path, hole formulation
             st_b = orc.RngState.from_seed(t)
             rc, x = _solve(shim, f0, fs, s, st_b, force_general)
             if err:
@@ -154,3 +155,40 @@ def test_device_single_constraint_deterministic_choice(shim):
             assert not drew and want == out.value, (t, f0, (p, q, r, rel), s, want, out.value)
         else:
             assert want is None and not drew, (t, f0, (p, q, r, rel), s, want)
+
+
+def test_hole_formulation_heavy_ties(shim):
+    """The hole formulation (cd.cu's general path) on constraint sets built to collide: lattice coefficients, repeated constraints,
+    '==' pairs sharing roots with '<=' holes, levels that make roots coincide.  Result and RNG consumption must equal the oracle's."""
+    rs = np.random.RandomState(4242)
+    for t in range(3000):
+        m = int(rs.randint(2, 40))
+        fs = []
+        for _ in range(m):
+            p = float(rs.choice([-2.0, -1.0, -1.0, -0.5, 0.0, 1.0, 2.0]))
+            q = float(rs.randint(-3, 4))
+            r = float(rs.randint(-6, 3)) * float(rs.choice([1.0, 0.5, 0.25]))
+            if p == 0 and q == 0:
+                q = 1.0
+            fs.append((p, q, r, "==" if rs.rand() < 0.25 else "<="))
+        for _ in range(rs.randint(0, 4)):
+            fs[rs.randint(0, m)] = fs[rs.randint(0, m)]
+        k0 = rs.randint(0, 4)
+        f0 = (0.0, 0.0, 1.0) if k0 == 0 else (float(rs.randint(-2, 3)), float(rs.randint(-3, 4)), float(rs.randint(-3, 4)))
+        s = float(rs.choice([0.0, 0.25, 0.5, 1.0, 2.0, 4.0, 7.0]))
+        st_a = orc.RngState.from_seed(t)
+        try:
+            want = orc.onevar_qcqp(f0, fs, s, st_a)
+            err = False
+        except OverflowError:
+            err = True
+        st_b = orc.RngState.from_seed(t)
+        rc, x = _solve(shim, f0, fs, s, st_b, 2)
+        if err:
+            assert rc == -2, (t, f0, fs, s)
+            continue
+        if want is None:
+            assert rc == 0, (t, f0, fs, s, x)
+        else:
+            assert rc == 1 and x == want, (t, f0, fs, s, x, want)
+        assert st_a.pos == st_b.pos, (t, f0, fs, s)

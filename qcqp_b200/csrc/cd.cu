@@ -11,7 +11,9 @@
 // -> feasible set at level s (lanes over forms, fold + events) -> lane 0: sweep line + minimiser + RNG -> move and
 // incremental update f_j += ... of the incident forms.
 #include <cstdio>
+#include <cstdlib>
 
+#include "cd_holes.cuh"
 #include "cd_shared.cuh"
 #include "common.cuh"
 #include "forms_eval.cuh"
@@ -85,82 +87,6 @@ __device__ __forceinline__ double dense_row_dot_seq(const double* row, const dou
     return s;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Sweep line, GPU formulation (onevar.cuh "HOLE formulation" has the argument and the scalar statement that the CPU
-// tests hold against the reference): singles and hulls are folded into (L, H, mu); only the holes of two-interval
-// constraints are sorted -- by their start, 16-byte (a, b) records -- and one prefix-max scan of their ends yields
-// the feasible pieces in ascending order.  <= 32 holes: registers + shuffles; more: shared memory.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bitonic_sort_holes_smem(double2* h, int N, int lane)
-{
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 4
-            for (int t = lane; t < (N >> 1); t += 32) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const double2 a = h[i], b = h[p];
-                const bool up = ((i & k) == 0);
-                if ((a.x > b.x) == up && a.x != b.x) { h[i] = b; h[p] = a; }
-            }
-            __syncwarp();
-        }
-    }
-}
-__device__ __forceinline__ void bitonic_sort_holes_reg(double& a, double& b, int lane)
-{
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const double pa = __shfl_xor_sync(FULL, a, j), pb = __shfl_xor_sync(FULL, b, j);
-            const bool keepmin = (((lane & j) == 0) == ((lane & k) == 0));
-            const bool swap = keepmin ? (pa < a) : (pa > a);
-            if (swap) { a = pa; b = pb; }
-        }
-    }
-}
-
-struct HoleScan {
-    double carryM;    // max(L, ends of the holes of earlier chunks)          (warp-uniform)
-    double prevA;     // start of the last hole of the previous chunk         (warp-uniform)
-    bool havePrev;
-    bool blocked;     // per lane: one of my holes has a <= H <= b
-    double stH;       // per lane: max{b : b < H} over my holes
-    int nC;           // pieces written so far                                (warp-uniform)
-};
-
-// one chunk of 32 holes in ascending order of a (lane = position); nextA = start of the first hole of the next chunk
-__device__ __forceinline__ void scan_hole_chunk(const WarpMem& w, const Fold& f, double a, double b, double nextA, HoleScan& hs, int lane)
-{
-    double inc = b;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o && t > inc) inc = t;
-    }
-    const double exc = __shfl_up_sync(FULL, inc, 1);
-    double M = hs.carryM;
-    if (lane > 0 && exc > M) M = exc;
-    const double ap = __shfl_up_sync(FULL, a, 1);
-    const bool tiep = (lane > 0) ? (ap == a) : (hs.havePrev && hs.prevA == a);
-    double an = __shfl_down_sync(FULL, a, 1);
-    if (lane == 31) an = nextA;
-    const bool valid = !tiep && (an != a) && (M < a) && (a < f.H);
-    const unsigned vb = __ballot_sync(FULL, valid);
-    if (valid) {
-        const int pos = hs.nC + __popc(vb & ((1u << lane) - 1u));
-        w.clo[pos] = M; w.chi[pos] = a;
-    }
-    hs.nC += __popc(vb);
-    if (a <= f.H && f.H <= b) hs.blocked = true;
-    if (b < f.H && b > hs.stH) hs.stH = b;
-    const double tot = __shfl_sync(FULL, inc, 31);
-    if (tot > hs.carryM) hs.carryM = tot;
-    hs.prevA = __shfl_sync(FULL, a, 31);
-    hs.havePrev = true;
-}
-
 // tail of onevar_qcqp: f = the all-reduced fold (singles + hulls), nh holes -- in (ra, rb), one per lane, when
 // in_regs, else in w.hx[0..nh).  Lane 0 owns the RNG.  Returns found (warp-uniform); xout/err valid in every lane.
 __device__ __forceinline__ int holes_finish(const WarpMem& w, const Fold& f, int nh, bool in_regs, double ra, double rb, double p0, double q0,
@@ -184,7 +110,7 @@ __device__ __forceinline__ int holes_finish(const WarpMem& w, const Fold& f, int
                     if (lane < nh) { const double2 t = w.hx[lane]; a = t.x; b = t.y; }
                 }
                 bitonic_sort_holes_reg(a, b, lane);
-                scan_hole_chunk(w, f, a, b, QCQP_INF, hs, lane);
+                scan_hole_chunk(w.clo, w.chi, f, a, b, QCQP_INF, hs, lane);
             } else {
                 int N2 = 64;
                 while (N2 < nh) N2 <<= 1;
@@ -196,7 +122,7 @@ __device__ __forceinline__ int holes_finish(const WarpMem& w, const Fold& f, int
                 for (int c = 0; c < nchunk; c++) {
                     const double2 nxt = w.hx[(c + 1 < (N2 >> 5)) ? ((c + 1) << 5) + lane : lane];
                     const double nextA = (c + 1 < (N2 >> 5)) ? __shfl_sync(FULL, nxt.x, 0) : QCQP_INF;
-                    scan_hole_chunk(w, f, cur.x, cur.y, nextA, hs, lane);
+                    scan_hole_chunk(w.clo, w.chi, f, cur.x, cur.y, nextA, hs, lane);
                     cur = nxt;
                 }
             }
@@ -220,22 +146,6 @@ __device__ __forceinline__ int holes_finish(const WarpMem& w, const Fold& f, int
     *xout = bcast(xv, 0);
     *err = bcast_i(e, 0);
     return bcast_i(found, 0);
-}
-
-__device__ __forceinline__ void fold_allreduce(Fold& f)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double L2 = __shfl_xor_sync(FULL, f.L, o), H2 = __shfl_xor_sync(FULL, f.H, o);
-        int mu2 = __shfl_xor_sync(FULL, f.mu, o), m12 = __shfl_xor_sync(FULL, f.m1, o);
-        int mc2 = __shfl_xor_sync(FULL, f.mcnt, o), ne2 = __shfl_xor_sync(FULL, f.nempty, o);
-        f.merge(L2, H2, mu2, m12, mc2, ne2);
-    }
-}
-__device__ __forceinline__ void fold_bcast(Fold& f, int src)
-{
-    f.L = bcast(f.L, src); f.H = bcast(f.H, src); f.mu = bcast_i(f.mu, src); f.m1 = bcast_i(f.m1, src);
-    f.mcnt = bcast_i(f.mcnt, src); f.nempty = bcast_i(f.nempty, src);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1053,6 +963,16 @@ int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R,
 {
     if (R <= 0) return QCQP_OK;
     CdLayout L;
+    // CTA-per-restart kernel (cd_blk.cu): sparse problems whose coordinates meet many constraints; strict = 4 / 5 force it
+    // (fast / strict summation) for A/B runs and the parity tests at small sizes
+    if (prm->strict == 4 || prm->strict == 5 || ((prm->strict == 0 || prm->strict == 1) && !(prm->strict == 0 && p->lpc_ok) && blk_wanted(p))) {
+        CdK kb;
+        kb.num_iters = prm->num_iters; kb.viol_tol = prm->viol_tol; kb.tol = prm->tol; kb.phase1 = prm->phase1;
+        kb.mode = (prm->strict == 1 || prm->strict == 5) ? MODE_STRICT : MODE_FRESH;
+        kb.refresh_every = prm->refresh_every > 0 ? prm->refresh_every : 64;
+        const char* ft = getenv("QCQP_BLK_THREADS");
+        return blk_launch(p, kb, dX0, R, drng, dX, df0, dmv, dstats, stream, ft ? atoi(ft) : 0);
+    }
     const int mode = (prm->strict == 1) ? MODE_STRICT : (prm->strict == 2 ? MODE_FRESH : MODE_GRAD);
     if (prm->strict == 0 && p->lpc_ok) {
         // separable problem (one single-coordinate constraint per coordinate): the lane-per-coordinate kernel

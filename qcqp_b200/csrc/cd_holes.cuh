@@ -1,0 +1,102 @@
+// cd_holes.cuh -- warp-level pieces of the GPU sweep line shared by the coordinate-descent kernels (cd.cu: one warp per
+// restart; cd_blk.cu: one CTA per restart): sorting the holes of the two-interval constraints, the prefix-max scan that
+// turns sorted holes into feasible pieces, and the warp all-reduce of the single-interval fold (onevar.cuh has the argument).
+#pragma once
+#include "common.cuh"
+#include "onevar.cuh"
+
+namespace qcqp {
+
+// ---------------------------------------------------------------------------------------------------------
+// Sweep line, GPU formulation (onevar.cuh "HOLE formulation" has the argument and the scalar statement that the CPU
+// tests hold against the reference): singles and hulls are folded into (L, H, mu); only the holes of two-interval
+// constraints are sorted -- by their start, 16-byte (a, b) records -- and one prefix-max scan of their ends yields
+// the feasible pieces in ascending order.  <= 32 holes: registers + shuffles; more: shared memory.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_holes_smem(double2* h, int N, int lane)
+{
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 4
+            for (int t = lane; t < (N >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const double2 a = h[i], b = h[p];
+                const bool up = ((i & k) == 0);
+                if ((a.x > b.x) == up && a.x != b.x) { h[i] = b; h[p] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+__device__ __forceinline__ void bitonic_sort_holes_reg(double& a, double& b, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const double pa = __shfl_xor_sync(FULL, a, j), pb = __shfl_xor_sync(FULL, b, j);
+            const bool keepmin = (((lane & j) == 0) == ((lane & k) == 0));
+            const bool swap = keepmin ? (pa < a) : (pa > a);
+            if (swap) { a = pa; b = pb; }
+        }
+    }
+}
+
+struct HoleScan {
+    double carryM;    // max(L, ends of the holes of earlier chunks)          (warp-uniform)
+    double prevA;     // start of the last hole of the previous chunk         (warp-uniform)
+    bool havePrev;
+    bool blocked;     // per lane: one of my holes has a <= H <= b
+    double stH;       // per lane: max{b : b < H} over my holes
+    int nC;           // pieces written so far                                (warp-uniform)
+};
+
+// one chunk of 32 holes in ascending order of a (lane = position); nextA = start of the first hole of the next chunk
+__device__ __forceinline__ void scan_hole_chunk(double* clo, double* chi, const Fold& f, double a, double b, double nextA, HoleScan& hs, int lane)
+{
+    double inc = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o && t > inc) inc = t;
+    }
+    const double exc = __shfl_up_sync(FULL, inc, 1);
+    double M = hs.carryM;
+    if (lane > 0 && exc > M) M = exc;
+    const double ap = __shfl_up_sync(FULL, a, 1);
+    const bool tiep = (lane > 0) ? (ap == a) : (hs.havePrev && hs.prevA == a);
+    double an = __shfl_down_sync(FULL, a, 1);
+    if (lane == 31) an = nextA;
+    const bool valid = !tiep && (an != a) && (M < a) && (a < f.H);
+    const unsigned vb = __ballot_sync(FULL, valid);
+    if (valid) {
+        const int pos = hs.nC + __popc(vb & ((1u << lane) - 1u));
+        clo[pos] = M; chi[pos] = a;
+    }
+    hs.nC += __popc(vb);
+    if (a <= f.H && f.H <= b) hs.blocked = true;
+    if (b < f.H && b > hs.stH) hs.stH = b;
+    const double tot = __shfl_sync(FULL, inc, 31);
+    if (tot > hs.carryM) hs.carryM = tot;
+    hs.prevA = __shfl_sync(FULL, a, 31);
+    hs.havePrev = true;
+}
+
+__device__ __forceinline__ void fold_allreduce(Fold& f)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double L2 = __shfl_xor_sync(FULL, f.L, o), H2 = __shfl_xor_sync(FULL, f.H, o);
+        int mu2 = __shfl_xor_sync(FULL, f.mu, o), m12 = __shfl_xor_sync(FULL, f.m1, o);
+        int mc2 = __shfl_xor_sync(FULL, f.mcnt, o), ne2 = __shfl_xor_sync(FULL, f.nempty, o);
+        f.merge(L2, H2, mu2, m12, mc2, ne2);
+    }
+}
+__device__ __forceinline__ void fold_bcast(Fold& f, int src)
+{
+    f.L = bcast(f.L, src); f.H = bcast(f.H, src); f.mu = bcast_i(f.mu, src); f.m1 = bcast_i(f.m1, src);
+    f.mcnt = bcast_i(f.mcnt, src); f.nempty = bcast_i(f.nempty, src);
+}
+
+}  // namespace qcqp

@@ -15,4 +15,9 @@ struct CdK {
 int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0, double* dmv,
                qcqp_cd_stats* dstats, cudaStream_t stream);
 
+// cd_blk.cu: one CTA per restart (sparse forms only); blk_wanted: the dispatch rule of qcqp_cd_improve
+bool blk_wanted(const qcqp_pack* p);
+int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0, double* dmv,
+               qcqp_cd_stats* dstats, cudaStream_t stream, int force_threads);
+
 }  // namespace qcqp

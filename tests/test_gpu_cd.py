@@ -186,3 +186,79 @@ def test_phase1_fixed_point_is_fast_forwarded():
     assert st[0].steps_skipped > 0 and st[0].steps_p1 + st[0].steps_skipped == so.steps_p1
     assert np.array_equal(X[0], xo) and rng[0].pos == sto.pos and st[0].ran_phase2 == so.ran_phase2 == 0
     pack.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cd_blk.cu: one CTA per restart (many-incidence sparse problems).  strict = 5 / 4 force it at any size.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("threads", [128, 256, 512])
+@pytest.mark.parametrize("gen,gargs,R,kw", [
+    ("circle", dict(ncirc=3), 6, dict(num_iters=10)),
+    ("circle", dict(ncirc=6), 4, dict(num_iters=5)),
+    ("circle", dict(ncirc=20), 4, dict(num_iters=4)),      # 21 incidences per centre coordinate: register-sorted holes
+    ("circle", dict(ncirc=40), 3, dict(num_iters=3)),      # 39 holes per centre coordinate: block sort + chunked scan
+    ("circle", dict(ncirc=50), 2, dict(num_iters=2)),      # radius meets 1327 forms: coefficients recomputed per probe
+    ("random", dict(n=6, m=4, seed=0), 6, dict(num_iters=20)),
+    ("random", dict(n=9, m=12, seed=5, density=0.6), 6, dict(num_iters=15)),
+    ("random", dict(n=12, m=80, seed=7, density=0.5), 4, dict(num_iters=6)),   # up to 80 mixed-relop constraints per coordinate
+    ("maxcut", dict(n=25, p=0.2, seed=1), 4, dict(num_iters=20)),
+])
+def test_cd_blk_strict_matches_oracle(gen, gargs, R, kw, threads, monkeypatch):
+    """The CTA-per-restart kernel reproduces the oracle's run like the warp-per-restart kernel does: x to 1e-9, identical
+    stream positions and step counts, at every CTA width."""
+    monkeypatch.setenv("QCQP_BLK_THREADS", str(threads))
+    forms, _ = GEN[gen](**gargs)
+    n = forms[0][1].size
+    rs = np.random.RandomState(321)
+    X0 = rs.randn(R, n) if gen != "circle" else np.abs(rs.randn(R, n)) * 3 + 0.5
+    seeds = 2000 + np.arange(R)
+    (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, seeds, 5, **kw)
+    for r in range(R):
+        xo, fo, vo, so, st = out[r]
+        assert sg[r].status == so.status
+        assert (sg[r].steps_p1, sg[r].steps_p2, sg[r].steps_skipped) == (so.steps_p1, so.steps_p2, so.steps_skipped), (r, sg[r].steps_p1, so.steps_p1, sg[r].steps_p2, so.steps_p2)
+        assert rng_g[r].pos == st.pos, r
+        assert rel_close(Xg[r], xo, rtol=1e-9, atol=1e-9), r
+        assert rel_close(fg[r], fo, rtol=1e-9, atol=1e-9)
+        assert rel_close(vg[r], vo, rtol=1e-6, atol=1e-10)
+
+
+def test_cd_blk_equals_warp_kernel_bitwise():
+    """Both general kernels take the same decisions with the same arithmetic: identical x, f0, stream, statistics."""
+    from qcqp_b200 import engine
+    for gen, gargs, kw in [("circle", dict(ncirc=30), dict(num_iters=4)), ("random", dict(n=10, m=40, seed=3, density=0.7), dict(num_iters=8))]:
+        forms, _ = GEN[gen](**gargs)
+        n = forms[0][1].size
+        rs = np.random.RandomState(11)
+        X0 = rs.randn(5, n) if gen != "circle" else np.abs(rs.randn(5, n)) * 3 + 0.5
+        pack = engine.Pack(forms)
+        assert not pack_blk_default(pack)      # strict=1 runs the warp-per-restart kernel on these
+        ra, rb = engine.rng_states(seeds=np.arange(5)), engine.rng_states(seeds=np.arange(5))
+        Xa, fa, va, sa = pack.cd_improve(X0, ra, strict=1, **kw)
+        Xb, fb, vb, sb = pack.cd_improve(X0, rb, strict=5, **kw)
+        assert np.array_equal(Xa, Xb) and np.array_equal(fa, fb) and np.array_equal(va, vb)
+        for r in range(5):
+            assert ra[r].pos == rb[r].pos and (sa[r].steps_p1, sa[r].steps_p2, sa[r].updates_p2) == (sb[r].steps_p1, sb[r].steps_p2, sb[r].updates_p2)
+        pack.close()
+
+
+def pack_blk_default(pack):
+    return pack.info.n_dense == 0 and pack.info.incidences >= 48 * pack.n
+
+
+def test_cd_blk_default_dispatch_circle_60():
+    """60 circles: 61 incidences per centre coordinate on average -> qcqp_cd_improve picks the CTA-per-restart kernel by
+    itself (strict 0 and 1); fast mode within 1e-6 of the oracle, same step counts and stream."""
+    forms, _ = GEN["circle"](ncirc=60)
+    from qcqp_b200 import engine
+    pack = engine.Pack(forms)
+    assert pack_blk_default(pack)
+    pack.close()
+    rs = np.random.RandomState(4)
+    X0 = np.abs(rs.randn(3, 121)) * 3 + 0.5
+    for strict in (0, 1):
+        (Xg, fg, vg, sg, rng_g), out = _run_both(forms, X0, 10 + np.arange(3), strict, num_iters=2)
+        for r in range(3):
+            xo, fo, vo, so, st = out[r]
+            assert rng_g[r].pos == st.pos and (sg[r].steps_p1, sg[r].steps_p2) == (so.steps_p1, so.steps_p2)
+            assert rel_close(fg[r], fo, rtol=1e-6, atol=1e-9) and rel_close(vg[r], vo, rtol=1e-6, atol=1e-9)

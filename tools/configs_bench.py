@@ -34,15 +34,17 @@ out["C4_beamforming_N128_admm_16rho"] = dict(seconds=best, admm_iterations=int(i
                                              onecons_calls=int(sum(s.onecons_calls for s in st)), feasible_runs=int((mv < 1e-2).sum()),
                                              best_f0=float(f0[mv < 1e-2].min()) if (mv < 1e-2).any() else None)
 pack.close()
-# C5: circle packing 200 circles, N=401, m=20701; 64 restarts, 10 sweeps
+# C5: circle packing 200 circles, N=401, m=20701; 10 sweeps (mostly phase 1) and a phase-2-heavy run
 forms, _ = pb.circle_packing(200)
 pack = engine.Pack(forms)
-R = 64
-X0 = np.random.RandomState(5).randn(R, 401)
-rng = engine.rng_states(seeds=np.arange(R))
-t0 = time.perf_counter(); X, f0, mv, st = pack.cd_improve(X0, rng, num_iters=10); dt = time.perf_counter() - t0
-sweeps = sum(s.steps_p1 + s.steps_p2 for s in st) / 401.0
-out["C5_circle_200_R64_10sweeps"] = dict(seconds=dt, restart_sweeps=sweeps, restart_sweeps_per_s=sweeps / dt, max_violation=float(mv.max()),
-                                         bytes_per_sweep=pack.info.bytes_per_sweep_phase2)
+for R, iters in ((64, 10), (512, 10), (512, 40)):
+    X0 = np.random.RandomState(5).randn(R, 401)
+    rng = engine.rng_states(seeds=np.arange(R))
+    t0 = time.perf_counter(); X, f0, mv, st = pack.cd_improve(X0, rng, num_iters=iters); dt = time.perf_counter() - t0
+    sw1 = sum(s.steps_p1 for s in st) / 401.0; sw2 = sum(s.steps_p2 for s in st) / 401.0
+    out["C5_circle_200_R%d_%dsweeps" % (R, iters)] = dict(seconds=dt, restart_sweeps=sw1 + sw2, restart_sweeps_p1=sw1, restart_sweeps_p2=sw2,
+                                                          restart_sweeps_per_s=(sw1 + sw2) / dt, max_violation=float(mv.max()),
+                                                          best_r=float(-f0[mv < 1e-2].min()) if (mv < 1e-2).any() else None,
+                                                          bytes_per_sweep=pack.info.bytes_per_sweep_phase2)
 pack.close()
 print(json.dumps(out, indent=1))

@@ -21,8 +21,14 @@
 
 namespace qcqp {
 
+#ifdef BLK_PROF
+#define STAMP(c, slot) do { if ((c).on) { const long long now__ = clock64(); (c).prof[slot] += now__ - (c).last; (c).last = now__; } } while (0)
+#else
+#define STAMP(c, slot) do { } while (0)
+#endif
+
 struct BlkLayout {
-    int sc_cap;       // coefficient scratch entries in smem; coordinates with more incidences recompute them per probe
+    int sc_cap;       // coefficient scratch entries in smem; coordinates with more incidences use the per-restart HBM block
     int fval_smem;    // cached f_j in smem?
     int hcap;         // hole capacity (power of two, >= 64)
     unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_hx, o_clo, o_chi, o_wfd, o_wfi, o_cmax, o_ccnt, o_redd, o_redi, o_ictl,
@@ -31,19 +37,27 @@ struct BlkLayout {
 };
 
 enum { BPH_P1 = 0, BPH_P2 = 1, BPH_DONE = 2 };
-// ictl words: [0],[1] hole counters (by call parity), [2],[3] early-exit flags (by call parity), [4] found, [5] err, [6] nC
+// ictl words: [0],[1] hole counters (by call parity), [2],[3] early-exit flags (by call parity), [4] found, [5] err
 enum { IC_NH = 0, IC_FLAG = 2, IC_FOUND = 4, IC_ERR = 5 };
 
 struct BlkCtx {
     double* x; double* fval;
-    double* scp; double* scq; double* scr; int* screl;
     double2* hx; double* clo; double* chi;
     double* wfd; int* wfi;          // per-warp folds, two parities: [par][warp][2] and [par][warp][4]
     double* cmax; int* ccnt;        // per 32-hole chunk: max end, pieces found
     double* redd; int* redi;        // block reductions
     volatile int* ictl; double* dctl;
-    int tid, warp, lane, sc_cap;
+    int tid, warp, lane;
     int par;                        // call parity of solve_level
+#ifdef BLK_PROF
+    long long* prof; long long last; int on;
+#endif
+};
+
+// one-variable coefficients of the incident forms of the current coordinate: slot i belongs to thread i mod T.
+// rj = relop | form << 2.  Shared memory for coordinates with <= sc_cap incident forms, the restart's HBM block beyond.
+struct Scr {
+    double* p; double* q; double* r; int* rj;
 };
 
 template <int NW>
@@ -61,22 +75,38 @@ __device__ __forceinline__ void blk_max_sum(const BlkCtx& c, double& vmax, int& 
     vmax = mx; isum = s;
 }
 
-// (t2, t1, t0) of get_onevar_func (utilities.py:99-105) for incidence e; the row dot is summed by the owning thread in column
-// order with separately rounded multiply/add (SciPy's csr_matvec order, so strict and fast mode coincide here); t0 from the
-// cached f_j(x)
-__device__ __forceinline__ void blk_coeffs(const PackView& P, const BlkCtx& c, int e, double xk, double& p, double& q, double& r, int& rel,
-                                           int& j)
+// static metadata of one incidence (form word, diagonal, q_j[k], off-diagonal row with its first entry); fetched ahead of
+// its use, so that the only global round trip left inside a step is the gather of the cached f_j
+struct PMeta {
+    uint32_t fw;
+    int rbeg, rlen;
+    double t2, qk;
+};
+__device__ __forceinline__ PMeta blk_load_meta(const PackView& P, int e, bool valid)
 {
-    const uint32_t fw = P.inc_form[e];
-    j = (int)(fw & INC_FORM_MASK);
-    rel = (int)((fw >> INC_RELOP_SHIFT) & 3);
-    const double t2 = P.inc_t2[e], qk = P.inc_qk[e];
-    const int rbeg = P.inc_rbeg[e], rlen = P.inc_rlen[e];
+    PMeta mt;
+    mt.fw = 0xffffffffu; mt.rbeg = 0; mt.rlen = 0; mt.t2 = 0.0; mt.qk = 0.0;
+    if (valid) {
+        mt.fw = P.inc_form[e]; mt.rbeg = P.inc_rbeg[e]; mt.rlen = P.inc_rlen[e];
+        mt.t2 = P.inc_t2[e]; mt.qk = P.inc_qk[e];
+    }
+    return mt;
+}
+
+// (t2, t1, t0) of get_onevar_func (utilities.py:99-105) for one incidence; the row dot is summed by the owning thread in
+// column order with separately rounded multiply/add (SciPy's csr_matvec order, so strict and fast mode coincide here); t0
+// from the cached f_j(x).  The objective (form 0) is never a constraint: its slot holds (0, 0, 0), which the nfs filter drops.
+__device__ __forceinline__ void blk_coeffs_from(const PackView& P, const BlkCtx& c, const PMeta& mt, double xk, double& p, double& q,
+                                                double& r, int& rj)
+{
+    const int j = (int)(mt.fw & INC_FORM_MASK);
+    rj = (int)((mt.fw >> INC_RELOP_SHIFT) & 3) | (j << 2);
+    const double fv = c.fval[j];
     double dot = 0.0;
-    for (int t = rbeg; t < rbeg + rlen; t++) dot = dot + P.row_val[t] * c.x[P.row_col[t]];
-    const double t1 = 2 * dot + qk;
-    p = t2; q = t1;
-    r = c.fval[j] - xk * (t2 * xk + t1);
+    for (int t = mt.rbeg; t < mt.rbeg + mt.rlen; t++) dot = dot + P.row_val[t] * c.x[P.row_col[t]];
+    const double t1 = 2 * dot + mt.qk;
+    p = mt.t2; q = t1;
+    r = fv - xk * (mt.t2 * xk + t1);
 }
 
 // block bitonic sort of N2 (power of two, >= 64) holes by their start; stages whose partner distance stays inside a warp's
@@ -147,11 +177,11 @@ __device__ __forceinline__ bool blk_chunk_eval(const BlkCtx& c, const Fold& f, i
     return !tiep && (an != a) && (M < a) && (a < f.H);
 }
 
-// onevar_qcqp(f0 = (p0, q0, r0), the mk constraints of this coordinate, level s) by the whole CTA.  Returns found
+// onevar_qcqp(f0 = (p0, q0, r0), the cnt incident forms of this coordinate in sc, level s) by the whole CTA.  Returns found
 // (block-uniform); *xout / *err valid in every thread.
 template <int T>
-__device__ __forceinline__ int blk_solve_level(const PackView& P, BlkCtx& c, int cbeg, int mk, bool use_sc, double xk, double s, double p0,
-                                               double q0, double r0, MtRng& rng, double* xout, int* err)
+__device__ __forceinline__ int blk_solve_level(BlkCtx& c, const Scr& sc, int cnt, double s, double p0, double q0, double r0, MtRng& rng,
+                                               double* xout, int* err)
 {
     constexpr int NW = T / 32;
     *xout = 0.0;
@@ -163,42 +193,48 @@ __device__ __forceinline__ int blk_solve_level(const PackView& P, BlkCtx& c, int
     Fold f;
     f.init();
     const unsigned lt = (1u << c.lane) - 1u;
-    int it = 0;
-    for (int base = c.warp * 32; base < mk; base += T, it++) {
-        const int i = base + c.lane;
-        bool hole = false;
-        Hole hh;
-        hh.a = hh.b = 0.0;
-        if (i < mk) {
-            double p, q, r;
-            int rel, j;
-            if (use_sc) { p = c.scp[i]; q = c.scq[i]; r = c.scr[i]; rel = c.screl[i]; }
-            else blk_coeffs(P, c, cbeg + i, xk, p, q, r, rel, j);
-            if (!(p == 0.0 && q == 0.0)) {   // nfs filter of qcqp.py:116,166
+    {
+        // my slots, one per round, the next one's coefficients in flight while this one is folded
+        int i = c.warp * 32 + c.lane;
+        double pn = 0.0, qn = 0.0, rn = 0.0;
+        int rjn = 0;
+        if (i < cnt) { pn = sc.p[i]; qn = sc.q[i]; rn = sc.r[i]; rjn = sc.rj[i]; }
+        int it = 0;
+        for (int base = c.warp * 32; base < cnt; base += T, it++) {
+            const double p = pn, q = qn, r = rn;
+            const int rel = rjn & 3;
+            i += T;
+            pn = 0.0; qn = 0.0; rn = 0.0; rjn = 0;
+            if (i < cnt) { pn = sc.p[i]; qn = sc.q[i]; rn = sc.r[i]; rjn = sc.rj[i]; }
+            bool hole = false;
+            Hole hh;
+            hh.a = hh.b = 0.0;
+            if (!(p == 0.0 && q == 0.0)) {   // nfs filter of qcqp.py:116,166 (also drops the objective's and the empty slots)
                 Ival I[2];
-                const int cnt = feasible_intervals(p, q, r, rel, s, I);
-                hole = fold_constraint(f, cnt, I, &hh);
+                const int ni = feasible_intervals(p, q, r, rel, s, I);
+                hole = fold_constraint(f, ni, I, &hh);
             }
-        }
-        const unsigned hb = __ballot_sync(FULL, hole);
-        if (hb) {
-            int pos0 = 0;
-            if (c.lane == 0) pos0 = atomicAdd((int*)nh_ctr, __popc(hb));
-            pos0 = __shfl_sync(FULL, pos0, 0);
-            if (hole) c.hx[pos0 + __popc(hb & lt)] = make_double2(hh.a, hh.b);
-        }
-        // a constraint with no feasible point at this level, or an empty partial intersection of the singles: the final set
-        // is empty whatever the other warps find (long lists only: the radius of circle packing meets 20 701 constraints)
-        if (base + T < mk) {
-            bool bad = __any_sync(FULL, f.nempty > 0);
-            if (!bad && (it & 3) == 3) {
-                const double Lp = warp_max(f.L), Hp = -warp_max(-f.H);
-                bad = !(Lp < Hp);
+            const unsigned hb = __ballot_sync(FULL, hole);
+            if (hb) {
+                int pos0 = 0;
+                if (c.lane == 0) pos0 = atomicAdd((int*)nh_ctr, __popc(hb));
+                pos0 = __shfl_sync(FULL, pos0, 0);
+                if (hole) c.hx[pos0 + __popc(hb & lt)] = make_double2(hh.a, hh.b);
             }
-            if (bad) *flag = 1;
-            if (*flag) break;
+            // a constraint with no feasible point at this level, or an empty partial intersection of the singles: the final
+            // set is empty whatever the other warps find (long lists only: circle packing's radius meets 20 701 constraints)
+            if ((it & 3) == 3 && base + T < cnt) {
+                bool bad = __any_sync(FULL, f.nempty > 0);
+                if (!bad) {
+                    const double Lp = warp_max(f.L), Hp = -warp_max(-f.H);
+                    bad = !(Lp < Hp);
+                }
+                if (bad) *flag = 1;
+                if (*flag) break;
+            }
         }
     }
+    STAMP(c, 12);
     fold_allreduce(f);
     if (c.lane == 0) {
         double* wd = c.wfd + (size_t)(par * NW + c.warp) * 2;
@@ -213,6 +249,7 @@ __device__ __forceinline__ int blk_solve_level(const PackView& P, BlkCtx& c, int
         const int* wi = c.wfi + (size_t)(par * NW + w) * 4;
         f.merge(wd[0], wd[1], wi[0], wi[1], wi[2], wi[3]);
     }
+    STAMP(c, 13);
     const int nh = *nh_ctr;
     if (c.tid == 0) { c.ictl[IC_NH + (par ^ 1)] = 0; c.ictl[IC_FLAG + (par ^ 1)] = 0; }   // the next call's slots
     if (f.mcnt > 0 && (f.nempty > 0 || !(f.L < f.H))) return 0;   // the running total never gets full
@@ -291,6 +328,7 @@ __device__ __forceinline__ int blk_solve_level(const PackView& P, BlkCtx& c, int
             }
         }
     }
+    STAMP(c, 14);
     if (c.tid == 0) {
         int e = 0;
         double xv = 0.0;
@@ -299,39 +337,47 @@ __device__ __forceinline__ int blk_solve_level(const PackView& P, BlkCtx& c, int
         c.ictl[IC_FOUND] = found;
         c.ictl[IC_ERR] = e;
     }
+    STAMP(c, 15);
     __syncthreads();   // #2
+    STAMP(c, 16);
     *xout = c.dctl[0];
     *err = c.ictl[IC_ERR];
     return c.ictl[IC_FOUND];
 }
 
 // cached f_j(x) from scratch for forms j >= j0 (warps take blocks of 32 forms, same per-form summation as cd.cu's
-// refresh_fvals); returns the max constraint violation
+// refresh_fvals); returns the max constraint violation.  One copy, called from every sweep boundary.
 template <int T>
-__device__ __forceinline__ double blk_refresh_fvals(const PackView& P, const BlkCtx& c, int j0, bool strict)
+__device__ __noinline__ double blk_refresh_fvals(const PackView& P, const double* x, double* fv, double* redd, int j0, int strict)
 {
     constexpr int NW = T / 32;
-    double* fv = c.fval;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __syncthreads();
-    for (int base = j0 + c.warp * 32; base <= P.m; base += NW * 32) {
+    for (int base = j0 + warp * 32; base <= P.m; base += NW * 32) {
         const int hi = (base + 31 < P.m) ? base + 31 : P.m;
-        eval_forms(P, c.x, base, hi, strict, c.lane, [&](int j, double v) { fv[j] = v; }, false);
+        eval_forms(P, x, base, hi, strict != 0, lane, [&](int j, double v) { fv[j] = v; }, false);
     }
     __syncthreads();
     double mv = -QCQP_INF;
-    for (int j = 1 + c.tid; j <= P.m; j += T) {
+    for (int j = 1 + tid; j <= P.m; j += T) {
         const double v = violation_of(P.relop[j], fv[j]);
         mv = (v > mv) ? v : mv;
     }
-    int dummy = 0;
-    blk_max_sum<NW>(c, mv, dummy);
-    return mv;
+    mv = warp_max(mv);
+    if (lane == 0) redd[warp] = mv;
+    __syncthreads();
+    double mx = redd[0];
+#pragma unroll
+    for (int i = 1; i < NW; i++) { const double v = redd[i]; mx = (v > mx) ? v : mx; }
+    __syncthreads();
+    return mx;
 }
 
 template <int T>
-__global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(PackView P, CdK prm, BlkLayout lay, const double* __restrict__ X0, int R,
-                                                            qcqp_rng_state* rngs, double* __restrict__ X, double* __restrict__ f0_out,
-                                                            double* __restrict__ mv_out, qcqp_cd_stats* stats_out, double* ws_fval)
+__global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(const __grid_constant__ PackView P, CdK prm, BlkLayout lay,
+                                                            const double* __restrict__ X0, int R, qcqp_rng_state* rngs, double* __restrict__ X,
+                                                            double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out,
+                                                            double* ws_fval, double* ws_scr, int* ws_scrj)
 {
     constexpr int NW = T / 32;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -342,10 +388,18 @@ __global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(PackView P, CdK prm,
     c.x = reinterpret_cast<double*>(smem + lay.o_x);
     c.fval = lay.fval_smem ? reinterpret_cast<double*>(smem + lay.o_fval) : ws_fval + rr * (size_t)(m + 1);
     uint32_t* mt = reinterpret_cast<uint32_t*>(smem + lay.o_mt);
-    c.scp = reinterpret_cast<double*>(smem + lay.o_scp);
-    c.scq = reinterpret_cast<double*>(smem + lay.o_scq);
-    c.scr = reinterpret_cast<double*>(smem + lay.o_scr);
-    c.screl = reinterpret_cast<int*>(smem + lay.o_screl);
+    Scr sc_s, sc_g;
+    sc_s.p = reinterpret_cast<double*>(smem + lay.o_scp);
+    sc_s.q = reinterpret_cast<double*>(smem + lay.o_scq);
+    sc_s.r = reinterpret_cast<double*>(smem + lay.o_scr);
+    sc_s.rj = reinterpret_cast<int*>(smem + lay.o_screl);
+    sc_g = sc_s;
+    if (P.max_inc > lay.sc_cap) {
+        sc_g.p = ws_scr + rr * 3 * (size_t)P.max_inc;
+        sc_g.q = sc_g.p + P.max_inc;
+        sc_g.r = sc_g.q + P.max_inc;
+        sc_g.rj = ws_scrj + rr * (size_t)P.max_inc;
+    }
     c.hx = reinterpret_cast<double2*>(smem + lay.o_hx);
     c.clo = reinterpret_cast<double*>(smem + lay.o_clo);
     c.chi = reinterpret_cast<double*>(smem + lay.o_chi);
@@ -357,7 +411,6 @@ __global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(PackView P, CdK prm,
     c.redi = reinterpret_cast<int*>(smem + lay.o_redi);
     c.ictl = reinterpret_cast<volatile int*>(smem + lay.o_ictl);
     c.dctl = reinterpret_cast<double*>(smem + lay.o_dctl);
-    c.sc_cap = lay.sc_cap;
     c.par = 0;
     const int tid = c.tid;
 
@@ -372,169 +425,217 @@ __global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(PackView P, CdK prm,
     qcqp_cd_stats st;
     st.steps_p1 = st.steps_p2 = st.updates_p1 = st.updates_p2 = st.steps_skipped = 0;
     st.sweeps_p1 = st.sweeps_p2 = 0; st.status = QCQP_RUN_OK; st.ran_phase2 = 0;
-    const bool strict = (prm.mode == MODE_STRICT);
+    const int strict = (prm.mode == MODE_STRICT) ? 1 : 0;
     const double tol = prm.tol, viol_tol = prm.viol_tol;
+#ifdef BLK_PROF
+    long long prof[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    c.prof = prof; c.on = 0; c.last = 0;
+#endif
     int phase = BPH_P1;
     int t = 0;                    // sweeps done in the current phase
     long long update_counter = 0;
     double viol_last = QCQP_INF;  // phase 1
     double viol_p2 = 0.0;         // phase 2: frozen at entry (qcqp.py:157)
     const bool p1_over = !prm.phase1;
+    // sweep-boundary actions are folded into one evaluation site: what = 0 none, 1 phase-1 start (j0 = 1),
+    // 2 phase-1 -> phase-2 test (j0 = 0), 3 end of a phase-1 sweep (j0 = 1), 4 periodic phase-2 refresh (j0 = 0), 5 final (j0 = 0)
+    int what = 0;
+    bool skip = false;            // phase 1 'failed' break: the rest of the sweep is not executed (qcqp.py:138-141)
+    long long upd_before = 0;
+    double final_mv = 0.0;
 
     for (;;) {
-        // ---------------- sweep boundary: phase transitions (block-uniform) ----------------
-        if (phase == BPH_P1) {
-            if (p1_over || t >= prm.num_iters || viol_last < viol_tol) {
+        // ---------------- sweep boundary (block-uniform) ----------------
+        if (what == 0) {
+            if (phase == BPH_P1) what = (p1_over || t >= prm.num_iters || viol_last < viol_tol) ? 2 : (t == 0 ? 1 : 0);
+            else if (phase == BPH_DONE) what = 5;
+        }
+        if (what != 0) {
+            const double mv = blk_refresh_fvals<T>(P, c.x, c.fval, c.redd, (what == 1 || what == 3) ? 1 : 0, strict);
+            const int w = what;
+            what = 0;
+            if (w == 2) {
                 // improve_coord_descent: if max(prob.violations(x)) < viol_tol: phase 2   (qcqp.py:189-190)
-                const double mv = blk_refresh_fvals<T>(P, c, 0, strict);
                 if (m == 0) { st.status = QCQP_RUN_EMPTY_MAX; phase = BPH_DONE; }
                 else if (mv < viol_tol) { phase = BPH_P2; viol_p2 = mv; t = 0; update_counter = 0; st.ran_phase2 = 1; }
                 else phase = BPH_DONE;
-            } else if (t == 0) {
-                blk_refresh_fvals<T>(P, c, 1, strict);
+                if (phase == BPH_DONE) { what = 5; continue; }
+            } else if (w == 3) {
+                viol_last = mv;   // viol = max(prob.violations(x))  (qcqp.py:142)
+                t++;
+                if (!skip && st.updates_p1 == upd_before && !(viol_last < viol_tol) && t < prm.num_iters) {
+                    // a full sweep that moved nothing drew no random number either: every remaining iteration of qcqp.py:110
+                    // would repeat it exactly (cd.cu has the argument)
+                    st.steps_skipped += (long long)(prm.num_iters - t) * n;
+                    t = prm.num_iters;
+                }
+                continue;
+            } else if (w == 5) {
+                final_mv = mv;
+                break;
             }
         }
-        if (phase == BPH_P2 && t >= prm.num_iters) phase = BPH_DONE;
-        if (phase == BPH_DONE) break;
+        if (phase == BPH_P2 && t >= prm.num_iters) { phase = BPH_DONE; continue; }
         if (phase == BPH_P1) st.sweeps_p1++;
         if (phase == BPH_P2) st.sweeps_p2++;
-        bool skip = false;   // phase 1 'failed' break: the rest of this sweep is not executed (qcqp.py:138-141)
-        const long long upd_before = st.updates_p1;
+        skip = false;
+        upd_before = st.updates_p1;
 
+        // incidence ranges and the static metadata of this thread's first two slots run one coordinate ahead of the work
+        int pb0 = P.inc_ptr[0], pb1 = P.inc_ptr[1], pb2 = P.inc_ptr[n >= 2 ? 2 : 1];
+        PMeta pf0 = blk_load_meta(P, pb0 + tid, pb0 + tid < pb1);
+        PMeta pf1 = blk_load_meta(P, pb0 + tid + T, pb0 + tid + T < pb1);
         for (int k = 0; k < n && phase != BPH_DONE && !skip; k++) {
-            const int beg = P.inc_ptr[k], end = P.inc_ptr[k + 1];
-            const bool obj_inc = (end > beg) && ((P.inc_form[beg] & INC_FORM_MASK) == 0);   // the objective, when incident, comes first
-            const int cbeg = beg + (obj_inc ? 1 : 0);
-            const int mk = end - cbeg;
-            const bool use_sc = mk <= c.sc_cap;
+#ifdef BLK_PROF
+            c.on = (phase == BPH_P2 && pb1 - pb0 <= lay.sc_cap); c.last = clock64();
+#endif
+            const PMeta cur0 = pf0, cur1 = pf1;
+            const int beg = pb0, end = pb1;
+            pb0 = pb1; pb1 = pb2;
+            if (k + 3 <= n) pb2 = P.inc_ptr[k + 3];
+            pf0 = blk_load_meta(P, pb0 + tid, (k + 1 < n) && (pb0 + tid < pb1));
+            pf1 = blk_load_meta(P, pb0 + tid + T, (k + 1 < n) && (pb0 + tid + T < pb1));
+            STAMP(c, 10);
+            const int cnt = end - beg;            // incident forms; the objective, when incident, is slot 0 (thread 0's)
+            const Scr sc = (cnt <= lay.sc_cap) ? sc_s : sc_g;
             const double xk = c.x[k];
+            const bool in_p1 = (phase == BPH_P1);
+            // objective coefficients: thread 0 only (it owns slot 0 and the RNG); phase 1 never looks at the objective
+            const bool obj_mine = (tid == 0) && (cnt > 0) && ((cur0.fw & INC_FORM_MASK) == 0);
+            double p0 = 0.0, q0 = 0.0, r0 = 0.0;
+            // ---- coefficients of my slots (tid, tid + T, ...): private to this thread until the next coordinate ----
+            if (tid < cnt) {
+                double p, q, r;
+                int rj;
+                blk_coeffs_from(P, c, cur0, xk, p, q, r, rj);
+                if (obj_mine) {
+                    if (!in_p1) { p0 = p; q0 = q; r0 = r; }
+                    p = 0.0; q = 0.0; r = 0.0; rj = 0;
+                }
+                sc.p[tid] = p; sc.q[tid] = q; sc.r[tid] = r; sc.rj[tid] = rj;
+            }
+            if (tid + T < cnt) {
+                double p, q, r;
+                int rj;
+                blk_coeffs_from(P, c, cur1, xk, p, q, r, rj);
+                sc.p[tid + T] = p; sc.q[tid + T] = q; sc.r[tid + T] = r; sc.rj[tid + T] = rj;
+            }
+            if (tid + 2 * T < cnt) {
+                // long lists: metadata two rounds ahead, the cached f_j one round ahead of the arithmetic
+                int i = tid + 2 * T;
+                PMeta m0 = blk_load_meta(P, beg + i, true);
+                PMeta m1 = blk_load_meta(P, beg + i + T, i + T < cnt);
+                double fv0 = c.fval[m0.fw & INC_FORM_MASK];
+                for (; i < cnt; i += T) {
+                    const PMeta m2 = blk_load_meta(P, beg + i + 2 * T, i + 2 * T < cnt);
+                    const double fv1 = (i + T < cnt) ? c.fval[m1.fw & INC_FORM_MASK] : 0.0;
+                    const int j = (int)(m0.fw & INC_FORM_MASK);
+                    double dot = 0.0;
+                    for (int u = m0.rbeg; u < m0.rbeg + m0.rlen; u++) dot = dot + P.row_val[u] * c.x[P.row_col[u]];
+                    const double t1 = 2 * dot + m0.qk;
+                    sc.p[i] = m0.t2; sc.q[i] = t1; sc.r[i] = fv0 - xk * (m0.t2 * xk + t1);
+                    sc.rj[i] = (int)((m0.fw >> INC_RELOP_SHIFT) & 3) | (j << 2);
+                    m0 = m1; m1 = m2; fv0 = fv1;
+                }
+            }
+            STAMP(c, 11);
+            // ---- the probes: phase 1 bisects the violation level (qcqp.py:113-141), phase 2 asks once at the frozen level
+            //      (qcqp.py:162-176); one call site, so the solver's code exists once ----
             double new_xi = xk;
             bool move = false;
             bool dead = false;   // the reference would have raised: stop this restart, leave x as it was
-            double p0 = 0.0, q0 = 0.0, r0 = 0.0;
-            if (phase == BPH_P2) {
-                r0 = c.fval[0];
-                if (obj_inc) {
-                    const int orb = P.inc_rbeg[beg], orl = P.inc_rlen[beg];
-                    double dot = 0.0;
-                    if (strict || orl <= 64) {
-                        for (int u = orb; u < orb + orl; u++) dot = dot + P.row_val[u] * c.x[P.row_col[u]];
-                    } else {
-                        double part = 0.0;
-                        for (int u = orb + tid; u < orb + orl; u += T) part = fma(P.row_val[u], c.x[P.row_col[u]], part);
-                        part = warp_sum(part);
-                        if (c.lane == 0) c.redd[c.warp] = part;
-                        __syncthreads();
-                        for (int w = 0; w < NW; w++) dot += c.redd[w];
-                        __syncthreads();
-                    }
-                    p0 = P.inc_t2[beg];
-                    q0 = 2 * dot + P.inc_qk[beg];
-                    r0 = c.fval[0] - xk * (p0 * xk + q0);
-                }
-            }
-            // coefficients of my incidences (thread tid owns i = tid, tid + T, ...: the scratch entries are private to it)
-            if (use_sc) {
-                for (int i = tid; i < mk; i += T) {
-                    double p, q, r;
-                    int rel, j;
-                    blk_coeffs(P, c, cbeg + i, xk, p, q, r, rel, j);
-                    c.scp[i] = p; c.scq[i] = q; c.scr[i] = r; c.screl[i] = rel;
-                }
-            }
-            if (phase == BPH_P1) {
+            double viol = 0.0, new_viol = 0.0, ss = 0.0, es = 0.0;
+            if (in_p1) {
                 st.steps_p1++;
                 double vmax = -QCQP_INF;
                 int cz = 0;
-                for (int i = tid; i < mk; i += T) {
-                    double p, q, r;
-                    int rel, j;
-                    if (use_sc) { p = c.scp[i]; q = c.scq[i]; r = c.scr[i]; rel = c.screl[i]; }
-                    else blk_coeffs(P, c, cbeg + i, xk, p, q, r, rel, j);
+                for (int i = tid; i < cnt; i += T) {
+                    const double p = sc.p[i], q = sc.q[i];
                     if (p == 0.0 && q == 0.0) continue;
                     cz++;
-                    const double v = violation_of(rel, onevar_eval(p, q, r, xk));
+                    const double v = violation_of(sc.rj[i] & 3, onevar_eval(p, q, sc.r[i], xk));
                     vmax = (v > vmax) ? v : vmax;
                 }
                 blk_max_sum<NW>(c, vmax, cz);
                 if (cz == 0) { st.status = QCQP_RUN_EMPTY_MAX; dead = true; }
-                else {
-                    const double viol = vmax;
-                    double new_viol = viol;
-                    double ss = -tol, es = viol - viol_tol;
-                    while (es - ss > tol) {
-                        const double s = (ss + es) / 2;
-                        double xi;
-                        int err;
-                        const int ok = blk_solve_level<T>(P, c, cbeg, mk, use_sc, xk, s, 0.0, 0.0, 0.0, rng, &xi, &err);
-                        if (err) { st.status = err; dead = true; break; }
-                        if (!ok) ss = s;
-                        else { new_xi = xi; new_viol = s; es = s; }
-                    }
-                    if (!dead) {
-                        if (new_viol < viol) { move = true; update_counter = 0; st.updates_p1++; }
-                        else {
-                            update_counter++;
-                            if (update_counter == n) skip = true;
-                        }
-                    }
-                }
+                viol = vmax; new_viol = vmax;
+                ss = -tol; es = viol - viol_tol;
             } else {
                 st.steps_p2++;
+            }
+            bool asked = false;
+            while (!dead) {
+                double s;
+                if (in_p1) {
+                    if (!(es - ss > tol)) break;
+                    s = (ss + es) / 2;
+                } else {
+                    if (asked) break;
+                    s = viol_p2;
+                    asked = true;
+                }
                 double xi;
                 int err;
-                const int ok = blk_solve_level<T>(P, c, cbeg, mk, use_sc, xk, viol_p2, p0, q0, r0, rng, &xi, &err);
-                if (err) { st.status = err; dead = true; }
-                else if (ok && fabs(xi - xk) > tol) { move = true; new_xi = xi; update_counter = 0; st.updates_p2++; }
-                else {
+                const int ok = blk_solve_level<T>(c, sc, cnt, s, p0, q0, r0, rng, &xi, &err);
+                if (err) { st.status = err; dead = true; break; }
+                if (in_p1) {
+                    if (!ok) ss = s;
+                    else { new_xi = xi; new_viol = s; es = s; }
+                } else if (ok && fabs(xi - xk) > tol) {
+                    move = true; new_xi = xi;
+                }
+            }
+            if (!dead) {
+                if (in_p1) {
+                    if (new_viol < viol) { move = true; update_counter = 0; st.updates_p1++; }
+                    else {
+                        update_counter++;
+                        if (update_counter == n) skip = true;
+                    }
+                } else if (move) {
+                    update_counter = 0; st.updates_p2++;
+                } else {
                     update_counter++;
                     if (update_counter == n) phase = BPH_DONE;   // converged
                 }
             }
+            STAMP(c, 17);
             if (move) {
-                // f_j(x) = t0 + b (t2 b + t1) for every incident form
+                // f_j(x) = t0 + b (t2 b + t1) for every incident constraint (and, in phase 2, the objective)
                 const double b = new_xi;
-                for (int i = tid; i < mk; i += T) {
-                    double p, q, r;
-                    int rel, j;
-                    if (use_sc) { p = c.scp[i]; q = c.scq[i]; r = c.scr[i]; j = (int)(P.inc_form[cbeg + i] & INC_FORM_MASK); }
-                    else blk_coeffs(P, c, cbeg + i, xk, p, q, r, rel, j);
-                    c.fval[j] = r + b * (p * b + q);
+                for (int i = tid; i < cnt; i += T) {
+                    const int j = sc.rj[i] >> 2;
+                    if (j > 0) c.fval[j] = sc.r[i] + b * (sc.p[i] * b + sc.q[i]);
                 }
                 if (tid == 0) {
-                    if (phase != BPH_P1 && obj_inc) c.fval[0] = r0 + b * (p0 * b + q0);
+                    if (!in_p1 && obj_mine) c.fval[0] = r0 + b * (p0 * b + q0);
                     c.x[k] = new_xi;
                 }
             }
             if (dead) phase = BPH_DONE;
+            STAMP(c, 18);
             __syncthreads();   // x and the cached f_j are current for the next coordinate
+            STAMP(c, 19);
         }
         // ---------------- end of sweep ----------------
-        if (phase == BPH_P1) {
-            const double mv = blk_refresh_fvals<T>(P, c, 1, strict);   // viol = max(prob.violations(x))  (qcqp.py:142)
-            viol_last = mv;
+        if (phase == BPH_P1) what = 3;
+        else if (phase == BPH_P2) {
             t++;
-            if (!skip && st.updates_p1 == upd_before && !(viol_last < viol_tol) && t < prm.num_iters) {
-                // a full sweep that moved nothing drew no random number either: every remaining iteration of qcqp.py:110
-                // would repeat it exactly (cd.cu has the argument)
-                st.steps_skipped += (long long)(prm.num_iters - t) * n;
-                t = prm.num_iters;
-            }
-        } else if (phase == BPH_P2) {
-            t++;
-            if (prm.refresh_every > 0 && (t % prm.refresh_every) == 0) blk_refresh_fvals<T>(P, c, 0, strict);
+            if (prm.refresh_every > 0 && (t % prm.refresh_every) == 0) what = 4;
         }
     }
 
     // ---------------- results: x, (f0.eval(x), max(violations(x))) as QCQP._improve returns them (qcqp.py:415-417) -------
-    const double mv = blk_refresh_fvals<T>(P, c, 0, strict);
     for (int i = tid; i < n; i += T) X[rr * n + i] = c.x[i];
     for (int i = tid; i < 624; i += T) rngs[rr].key[i] = mt[i];
     if (tid == 0) {
         rngs[rr].pos = rng.pos;
         f0_out[rr] = c.fval[0];
-        mv_out[rr] = (m > 0) ? mv : 0.0;
+        mv_out[rr] = (m > 0) ? final_mv : 0.0;
         if (stats_out) stats_out[rr] = st;
+#ifdef BLK_PROF
+        if (rr == 0) for (int i = 10; i < 20; i++) printf("prof[%d] = %lld (%.0f / p2 step)\n", i, prof[i], (double)prof[i] / (double)(st.steps_p2 > 0 ? st.steps_p2 : 1));
+#endif
     }
 }
 
@@ -552,10 +653,10 @@ bool blk_wanted(const qcqp_pack* p)
 
 template <int T>
 static int blk_launch_t(qcqp_pack* p, const CdK& k, const BlkLayout& L, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0,
-                        double* dmv, qcqp_cd_stats* dstats, double* ws_fval, cudaStream_t stream)
+                        double* dmv, qcqp_cd_stats* dstats, double* ws_fval, double* ws_scr, int* ws_scrj, cudaStream_t stream)
 {
     QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_blk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    cd_blk_kernel<T><<<R, T, L.total, stream>>>(p->v, k, L, dX0, R, drng, dX, df0, dmv, dstats, ws_fval);
+    cd_blk_kernel<T><<<R, T, L.total, stream>>>(p->v, k, L, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj);
     QCQP_CUDA_TRY(cudaGetLastError());
     return QCQP_OK;
 }
@@ -599,12 +700,18 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     if (l.total > (unsigned)max_smem_optin(p->device))
         return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: per-restart state exceeds shared memory (too many two-interval constraints on one coordinate)");
     const size_t fval_bytes = l.fval_smem ? 0 : (size_t)R * (v.m + 1) * 8;
-    int rc = ensure_workspace(p, fval_bytes + 256);
+    const bool spill = v.max_inc > l.sc_cap;
+    const size_t scr_bytes = spill ? (size_t)R * 3 * v.max_inc * 8 : 0;
+    const size_t scrj_bytes = spill ? (size_t)R * v.max_inc * 4 : 0;
+    const size_t a1 = (fval_bytes + 255) & ~(size_t)255, a2 = (scr_bytes + 255) & ~(size_t)255;
+    int rc = ensure_workspace(p, a1 + a2 + scrj_bytes + 256);
     if (rc != QCQP_OK) return rc;
     double* ws_fval = (double*)p->ws;
-    if (T == 512) return blk_launch_t<512>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, stream);
-    if (T == 256) return blk_launch_t<256>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, stream);
-    return blk_launch_t<128>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, stream);
+    double* ws_scr = (double*)((char*)p->ws + a1);
+    int* ws_scrj = (int*)((char*)p->ws + a1 + a2);
+    if (T == 512) return blk_launch_t<512>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
+    if (T == 256) return blk_launch_t<256>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
+    return blk_launch_t<128>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
 }
 
 }  // namespace qcqp

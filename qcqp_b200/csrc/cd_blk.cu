@@ -242,13 +242,14 @@ __device__ __forceinline__ int blk_solve_level(BlkCtx& c, const Scr& sc, int cnt
         wd[0] = f.L; wd[1] = f.H; wi[0] = f.mu; wi[1] = f.m1; wi[2] = f.mcnt; wi[3] = f.nempty;
     }
     __syncthreads();   // #1: folds, holes and their count are in shared memory
+    // block fold: lane w of every warp picks up warp w's fold, then the same all-reduce (no second barrier)
     f.init();
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-        const double* wd = c.wfd + (size_t)(par * NW + w) * 2;
-        const int* wi = c.wfi + (size_t)(par * NW + w) * 4;
-        f.merge(wd[0], wd[1], wi[0], wi[1], wi[2], wi[3]);
+    if (c.lane < NW) {
+        const double* wd = c.wfd + (size_t)(par * NW + c.lane) * 2;
+        const int* wi = c.wfi + (size_t)(par * NW + c.lane) * 4;
+        f.L = wd[0]; f.H = wd[1]; f.mu = wi[0]; f.m1 = wi[1]; f.mcnt = wi[2]; f.nempty = wi[3];
     }
+    fold_allreduce(f);
     STAMP(c, 13);
     const int nh = *nh_ctr;
     if (c.tid == 0) { c.ictl[IC_NH + (par ^ 1)] = 0; c.ictl[IC_FLAG + (par ^ 1)] = 0; }   // the next call's slots

@@ -83,15 +83,46 @@ __device__ __forceinline__ void scan_hole_chunk(double* clo, double* chi, const 
     hs.havePrev = true;
 }
 
+// order-preserving map double -> uint64 (never fed NaN: the fold's L and H only ever take values that won a comparison)
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k)
+{
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+// warp max / min of a double with two REDUX instructions each (high word, then the low words of the lanes that hold it)
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long k)
+{
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, (hi == mh) ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k)
+{
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, (hi == mh) ? lo : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// all-reduce of the per-lane folds.  Same result as merging lane by lane (Fold::merge): L = max, H = min, mu = the
+// multiplicities of the lanes that hold H (lanes that folded nothing carry H = +inf with mu = 0), counts add up.
+// (-0.0 and +0.0 compare equal in the lane-by-lane merge and are ordered here; nothing downstream tells them apart.)
 __device__ __forceinline__ void fold_allreduce(Fold& f)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double L2 = __shfl_xor_sync(FULL, f.L, o), H2 = __shfl_xor_sync(FULL, f.H, o);
-        int mu2 = __shfl_xor_sync(FULL, f.mu, o), m12 = __shfl_xor_sync(FULL, f.m1, o);
-        int mc2 = __shfl_xor_sync(FULL, f.mcnt, o), ne2 = __shfl_xor_sync(FULL, f.nempty, o);
-        f.merge(L2, H2, mu2, m12, mc2, ne2);
-    }
+    const unsigned long long kh = dkey(f.H);
+    const unsigned long long kH = warp_min_key(kh);
+    f.L = dunkey(warp_max_key(dkey(f.L)));
+    f.mu = __reduce_add_sync(FULL, (kh == kH) ? f.mu : 0);
+    f.H = dunkey(kH);
+    f.m1 = __reduce_add_sync(FULL, f.m1);
+    f.mcnt = __reduce_add_sync(FULL, f.mcnt);
+    f.nempty = __reduce_add_sync(FULL, f.nempty);
 }
 __device__ __forceinline__ void fold_bcast(Fold& f, int src)
 {

@@ -79,31 +79,39 @@ __device__ __forceinline__ void blk_max_sum(const BlkCtx& c, double& vmax, int& 
 // its use, so that the only global round trip left inside a step is the gather of the cached f_j
 struct PMeta {
     uint32_t fw;
-    int rbeg, rlen;
-    double t2, qk;
+    int rbeg, rlen, col0;
+    double t2, qk, val0;
 };
 __device__ __forceinline__ PMeta blk_load_meta(const PackView& P, int e, bool valid)
 {
     PMeta mt;
-    mt.fw = 0xffffffffu; mt.rbeg = 0; mt.rlen = 0; mt.t2 = 0.0; mt.qk = 0.0;
+    mt.fw = 0xffffffffu; mt.rbeg = 0; mt.rlen = 0; mt.col0 = 0; mt.t2 = 0.0; mt.qk = 0.0; mt.val0 = 0.0;
     if (valid) {
         mt.fw = P.inc_form[e]; mt.rbeg = P.inc_rbeg[e]; mt.rlen = P.inc_rlen[e];
         mt.t2 = P.inc_t2[e]; mt.qk = P.inc_qk[e];
     }
     return mt;
 }
+// second phase of the prefetch, issued once rbeg / rlen have arrived: the first off-diagonal entry of the row
+__device__ __forceinline__ void blk_load_row0(const PackView& P, PMeta& mt)
+{
+    if (mt.rlen > 0) { mt.col0 = P.row_col[mt.rbeg]; mt.val0 = P.row_val[mt.rbeg]; }
+}
 
 // (t2, t1, t0) of get_onevar_func (utilities.py:99-105) for one incidence; the row dot is summed by the owning thread in
 // column order with separately rounded multiply/add (SciPy's csr_matvec order, so strict and fast mode coincide here); t0
-// from the cached f_j(x).  The objective (form 0) is never a constraint: its slot holds (0, 0, 0), which the nfs filter drops.
-__device__ __forceinline__ void blk_coeffs_from(const PackView& P, const BlkCtx& c, const PMeta& mt, double xk, double& p, double& q,
-                                                double& r, int& rj)
+// from the cached f_j(x) (fv, gathered by the caller so that the loads of several slots are in flight together).
+// The objective (form 0) is never a constraint: its slot holds (0, 0, 0), which the nfs filter drops.
+__device__ __forceinline__ void blk_coeffs_from(const PackView& P, const BlkCtx& c, const PMeta& mt, double fv, double xk, double& p,
+                                                double& q, double& r, int& rj)
 {
     const int j = (int)(mt.fw & INC_FORM_MASK);
     rj = (int)((mt.fw >> INC_RELOP_SHIFT) & 3) | (j << 2);
-    const double fv = c.fval[j];
     double dot = 0.0;
-    for (int t = mt.rbeg; t < mt.rbeg + mt.rlen; t++) dot = dot + P.row_val[t] * c.x[P.row_col[t]];
+    if (mt.rlen > 0) {
+        dot = dot + mt.val0 * c.x[mt.col0];
+        for (int t = mt.rbeg + 1; t < mt.rbeg + mt.rlen; t++) dot = dot + P.row_val[t] * c.x[P.row_col[t]];
+    }
     const double t1 = 2 * dot + mt.qk;
     p = mt.t2; q = t1;
     r = fv - xk * (mt.t2 * xk + t1);
@@ -266,7 +274,9 @@ __device__ __forceinline__ int blk_solve_level(BlkCtx& c, const Scr& sc, int cnt
             if (nh > 0) {
                 double a = QCQP_INF, b = QCQP_INF;
                 if (c.lane < nh) { const double2 t = c.hx[c.lane]; a = t.x; b = t.y; }
-                bitonic_sort_holes_reg(a, b, c.lane);
+                int kmax = 2;
+                while (kmax < nh) kmax <<= 1;
+                bitonic_sort_holes_reg(a, b, c.lane, kmax);
                 scan_hole_chunk(c.clo, c.chi, f, a, b, QCQP_INF, hs, c.lane);
             }
             nC = hs.nC;
@@ -486,6 +496,8 @@ __global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(const __grid_constan
         int pb0 = P.inc_ptr[0], pb1 = P.inc_ptr[1], pb2 = P.inc_ptr[n >= 2 ? 2 : 1];
         PMeta pf0 = blk_load_meta(P, pb0 + tid, pb0 + tid < pb1);
         PMeta pf1 = blk_load_meta(P, pb0 + tid + T, pb0 + tid + T < pb1);
+        blk_load_row0(P, pf0);
+        blk_load_row0(P, pf1);
         for (int k = 0; k < n && phase != BPH_DONE && !skip; k++) {
 #ifdef BLK_PROF
             c.on = (phase == BPH_P2 && pb1 - pb0 <= lay.sc_cap); c.last = clock64();
@@ -505,21 +517,20 @@ __global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(const __grid_constan
             const bool obj_mine = (tid == 0) && (cnt > 0) && ((cur0.fw & INC_FORM_MASK) == 0);
             double p0 = 0.0, q0 = 0.0, r0 = 0.0;
             // ---- coefficients of my slots (tid, tid + T, ...): private to this thread until the next coordinate ----
-            if (tid < cnt) {
-                double p, q, r;
-                int rj;
-                blk_coeffs_from(P, c, cur0, xk, p, q, r, rj);
+            {
+                const bool has0 = tid < cnt, has1 = tid + T < cnt;
+                const double fv0 = has0 ? c.fval[cur0.fw & INC_FORM_MASK] : 0.0;
+                const double fv1 = has1 ? c.fval[cur1.fw & INC_FORM_MASK] : 0.0;
+                double pa = 0.0, qa = 0.0, ra = 0.0, pb = 0.0, qb = 0.0, rb = 0.0;
+                int rja = 0, rjb = 0;
+                if (has0) blk_coeffs_from(P, c, cur0, fv0, xk, pa, qa, ra, rja);
+                if (has1) blk_coeffs_from(P, c, cur1, fv1, xk, pb, qb, rb, rjb);
                 if (obj_mine) {
-                    if (!in_p1) { p0 = p; q0 = q; r0 = r; }
-                    p = 0.0; q = 0.0; r = 0.0; rj = 0;
+                    if (!in_p1) { p0 = pa; q0 = qa; r0 = ra; }
+                    pa = 0.0; qa = 0.0; ra = 0.0; rja = 0;
                 }
-                sc.p[tid] = p; sc.q[tid] = q; sc.r[tid] = r; sc.rj[tid] = rj;
-            }
-            if (tid + T < cnt) {
-                double p, q, r;
-                int rj;
-                blk_coeffs_from(P, c, cur1, xk, p, q, r, rj);
-                sc.p[tid + T] = p; sc.q[tid + T] = q; sc.r[tid + T] = r; sc.rj[tid + T] = rj;
+                if (has0) { sc.p[tid] = pa; sc.q[tid] = qa; sc.r[tid] = ra; sc.rj[tid] = rja; }
+                if (has1) { sc.p[tid + T] = pb; sc.q[tid + T] = qb; sc.r[tid + T] = rb; sc.rj[tid + T] = rjb; }
             }
             if (tid + 2 * T < cnt) {
                 // long lists: metadata two rounds ahead, the cached f_j one round ahead of the arithmetic
@@ -614,6 +625,8 @@ __global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(const __grid_constan
                 }
             }
             if (dead) phase = BPH_DONE;
+            blk_load_row0(P, pf0);
+            blk_load_row0(P, pf1);
             STAMP(c, 18);
             __syncthreads();   // x and the cached f_j are current for the next coordinate
             STAMP(c, 19);

@@ -29,10 +29,12 @@ __device__ __forceinline__ void bitonic_sort_holes_smem(double2* h, int N, int l
         }
     }
 }
-__device__ __forceinline__ void bitonic_sort_holes_reg(double& a, double& b, int lane)
+// holes in lanes 0..kmax-1 (kmax a power of two <= 32), +inf pads elsewhere: the sub-network of the first kmax lanes is enough
+__device__ __forceinline__ void bitonic_sort_holes_reg(double& a, double& b, int lane, int kmax = 32)
 {
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
+        if (k > kmax) break;
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             const double pa = __shfl_xor_sync(FULL, a, j), pb = __shfl_xor_sync(FULL, b, j);

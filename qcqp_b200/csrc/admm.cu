@@ -5,6 +5,9 @@
 // "TODO: parallel x/u-updates", qcqp.py:234): warps take constraints round-robin; a projection is two coalesced
 // GEMV passes over Q_i / Q_i^T (lanes own output components) around a warp-shuffle bisection on the multiplier.
 // z, the z-update right-hand side and the best point live in shared memory; xs/us [m][n] per run in HBM/L2.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "forms_eval.cuh"
 #include "onevar.cuh"
@@ -295,6 +298,9 @@ __global__ void __launch_bounds__(ADMM_THREADS) admm_kernel(PackView P, AdmmK pr
     }
 }
 
+int admm_res_try(qcqp_pack* p, const qcqp_admm_params* prm, const double* drhos, const double* dZinv, int K, const double* dX0, int R, double* dX,
+                 double* df0, double* dmv, qcqp_admm_stats* dstats, cudaStream_t stream, bool* used);
+
 int admm_launch(qcqp_pack* p, const qcqp_admm_params* prm, const double* drhos, const double* dZinv, int K, const double* dX0, int R,
                 double* dX, double* df0, double* dmv, qcqp_admm_stats* dstats, cudaStream_t stream)
 {
@@ -302,6 +308,14 @@ int admm_launch(qcqp_pack* p, const qcqp_admm_params* prm, const double* drhos, 
     if (runs <= 0) return QCQP_OK;
     const PackView& v = p->v;
     if (v.m <= 0) return fail(QCQP_ERR_INVALID, "qcqp_admm_improve: the problem has no constraints");
+    // constraint-resident kernel (admm_res.cu) whenever Q_i fits one SM's shared memory and m CTAs fit the GPU;
+    // QCQP_ADMM_KERNEL=run forces the one-CTA-per-run kernel below (A/B runs, tests)
+    const char* force = getenv("QCQP_ADMM_KERNEL");
+    if (!(force && strcmp(force, "run") == 0)) {
+        bool used = false;
+        int rc0 = admm_res_try(p, prm, drhos, dZinv, K, dX0, R, dX, df0, dmv, dstats, stream, &used);
+        if (used || rc0 != QCQP_OK) return rc0;
+    }
     const int npad = (v.n + 1) & ~1;
     size_t smem = ((size_t)7 * npad + (size_t)ADMM_WARPS * 3 * npad + ADMM_WARPS + 4) * 8;
     if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_admm_improve: n too large for shared memory");

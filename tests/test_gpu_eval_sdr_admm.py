@@ -91,10 +91,13 @@ def test_sdr_device_rng_statistics():
     pack.close()
 
 
-def test_admm_goldens(golden):
+@pytest.mark.parametrize("kernel", ["resident", "run"])
+def test_admm_goldens(golden, kernel, monkeypatch):
     """G4 and the other improve_admm goldens of the reference: 1e-6 on (objective, max violation), same number of
-    one-constraint projections."""
+    one-constraint projections.  Both kernels: admm_res.cu (eigenbases resident in shared memory, CTA per constraint) and
+    admm.cu (CTA per run)."""
     from qcqp_b200 import engine
+    monkeypatch.setenv("QCQP_ADMM_KERNEL", kernel)
     for c in golden["admm"]:
         forms, _ = forms_of(c)
         pack = engine.Pack(forms)
@@ -110,10 +113,12 @@ def test_admm_goldens(golden):
         pack.close()
 
 
-def test_admm_rho_sweep_matches_oracle():
+@pytest.mark.parametrize("kernel", ["resident", "run"])
+def test_admm_rho_sweep_matches_oracle(kernel, monkeypatch):
     """K rho values x R starts in one launch (the C4 shape, reduced): every run against the oracle."""
     from oracle import oracle as orc
     from qcqp_b200 import engine, problems as pb
+    monkeypatch.setenv("QCQP_ADMM_KERNEL", kernel)
     forms, _ = pb.beamforming(n=12, m=6, l=3, seed=1)
     P = orc.Problem(forms); pack = engine.Pack(forms)
     rs = np.random.RandomState(4)

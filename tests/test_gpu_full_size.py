@@ -107,6 +107,33 @@ def test_c4_beamforming_n128_admm_rho_sweep():
     pack.close()
 
 
+@pytest.mark.parametrize("kernel", ["resident", "run"])
+def test_c4_admm_against_oracle_fixture(kernel, monkeypatch):
+    """C4 at full size against the CPU oracle's run of the same sweep (tests/golden/c4_admm_oracle.json): (f0, maxviol) to 1e-6
+    for every rho, identical iteration counts -- except, for the resident kernel, rho = sqrt(32) 2^-1.5 = 2.0000000000000004:
+    there phase 2 sits on a bifurcation (the REFERENCE itself runs all 1000 iterations at rho = 2.0 exactly, in a period-3 limit
+    cycle whose step length bottoms out at 0.0114 > tol = 0.01, while a 1-ulp change of rho -- or of the summation order of the
+    GEMVs -- makes the same iteration converge after ~300 steps).  The best point is found long before, so the returned pair is
+    unaffected; the count is only required to be a legal outcome."""
+    import json, os
+    from qcqp_b200 import engine, problems as pb
+    monkeypatch.setenv("QCQP_ADMM_KERNEL", kernel)
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c4_admm_oracle.json")))
+    forms, _ = pb.beamforming(n=64, m=24, l=8, seed=1)
+    pack = engine.Pack(forms)
+    rhos = np.array(g["rhos"])
+    X, f0, mv, st = pack.admm_improve(np.array(g["x0"])[None, :], rhos)
+    assert rel_close(f0.ravel(), g["f0"], rtol=1e-6, atol=1e-9) and rel_close(mv.ravel(), g["maxviol"], rtol=1e-6, atol=1e-8)
+    sensitive = {5} if kernel == "resident" else set()
+    for k in range(len(rhos)):
+        assert st[k].iters_p1 == g["iters_p1"][k], k
+        if k in sensitive:
+            assert 1 <= st[k].iters_p2 <= 1000
+        else:
+            assert st[k].iters_p2 == g["iters_p2"][k], (k, rhos[k], st[k].iters_p2, g["iters_p2"][k])
+    pack.close()
+
+
 def test_c5_circle_packing_200_circles():
     from qcqp_b200 import engine, problems as pb
     forms, _ = pb.circle_packing(200)

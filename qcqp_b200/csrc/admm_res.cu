@@ -129,36 +129,57 @@ struct ResSmem {
     int* flag;      // [RB] early-out / command
 };
 
-// the multiplier search of onecons_qcqp (utilities.py:168-195) by one warp; zhat = Q^T v in zh, result xhat
-__device__ __forceinline__ void res_bisect(const double* lam, const double* qh, const double* zhat, double* xhat, double r, int n, int lane)
+// the multiplier search of onecons_qcqp (utilities.py:168-195) by one warp; zhat = Q^T v, result xhat.
+// A lane keeps its (at most RES_EPL) eigen-components in registers for the ~65 evaluations of phi.
+constexpr int RES_EPL = 6;   // n <= 192 (shared memory holds Q_i up to n ~ 165)
+
+template <int NEL>
+__device__ __forceinline__ void res_bisect_t(const double* lam, const double* qh, const double* zhat, double* xhat, double r, int n, int lane)
 {
+    double L[NEL], Qh[NEL], Z2[NEL];
+#pragma unroll
+    for (int u = 0; u < NEL; u++) {
+        const int t = lane + 32 * u;
+        const bool ok = t < n;
+        L[u] = ok ? lam[t] : 0.0; Qh[u] = ok ? qh[t] : 0.0; Z2[u] = ok ? 2 * zhat[t] : 0.0;   // a padded slot adds exactly 0 to phi
+    }
     double s = -QCQP_INF, e = QCQP_INF;
-    for (int t = lane; t < n; t += 32) {
-        double l = lam[t];
+#pragma unroll
+    for (int u = 0; u < NEL; u++) {
+        const double l = L[u];
         if (l > 0) { double c = -1. / l; s = c > s ? c : s; }
         if (l < 0) { double c = -1. / l; e = c < e ? c : e; }
     }
     s = warp_max(s);
     e = -warp_max(-e);
     // phi(nu) = sum lambda xhat^2 + qhat.xhat + r (utilities.py:169-175).  Only its SIGN steers the search, so the quotient
-    // is taken with a reciprocal refined to full precision (1-2 ulp) instead of the 125-cycle IEEE division; the returned
-    // xhat((s+e)/2) below uses the exact division.
+    // is taken with a reciprocal refined to full precision (1-2 ulp) instead of the 125-cycle IEEE division (straight-line code:
+    // the NEL quotients overlap), and the two sums share one shuffle reduction.  A denominator outside the reciprocal's safe
+    // range sends the whole warp through the exact division.  The returned xhat((s+e)/2) below always uses the exact division.
     auto phi = [&](double nu) {
-        double a = 0.0, b = 0.0;
-        for (int t = lane; t < n; t += 32) {
-            const double num = nu * qh[t] - 2 * zhat[t], den = 2 * (1 + nu * lam[t]);
-            double xh;
-            if (fabs(den) > 1e-280 && fabs(den) < 1e280) {
-                double y;
-                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
-                double e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
-                e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
-                xh = -(num * y);
-            } else xh = -(num / den);
-            a = fma(lam[t], xh * xh, a);
-            b = fma(qh[t], xh, b);
+        double acc = 0.0;
+        bool odd = false;
+#pragma unroll
+        for (int u = 0; u < NEL; u++) {
+            const double num = nu * Qh[u] - Z2[u], den = 2 * (1 + nu * L[u]);
+            const double ad = fabs(den);
+            odd = odd || !(ad > 1e-280 && ad < 1e280);
+            double y;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+            double e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
+            e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
+            const double xh = -(num * y);
+            acc = fma(fma(L[u], xh, Qh[u]), xh, acc);
         }
-        return warp_sum(a) + warp_sum(b) + r;
+        if (__any_sync(FULL, odd)) {
+            acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < NEL; u++) {
+                const double xh = -((nu * Qh[u] - Z2[u]) / (2 * (1 + nu * L[u])));
+                acc = fma(fma(L[u], xh, Qh[u]), xh, acc);
+            }
+        }
+        return warp_sum(acc) + r;
     };
     int guard = 0;
     if (s == -QCQP_INF) { s = -1.; while (phi(s) <= 0 && ++guard < 4096) s *= 2.; }
@@ -172,6 +193,15 @@ __device__ __forceinline__ void res_bisect(const double* lam, const double* qh, 
     }
     const double nu = (s + e) / 2.;
     for (int t = lane; t < n; t += 32) xhat[t] = -((nu * qh[t] - 2 * zhat[t]) / (2 * (1 + nu * lam[t])));
+}
+
+__device__ __forceinline__ void res_bisect(const double* lam, const double* qh, const double* zhat, double* xhat, double r, int n, int lane)
+{
+    const int nel = (n + 31) >> 5;
+    if (nel <= 1) res_bisect_t<1>(lam, qh, zhat, xhat, r, n, lane);
+    else if (nel == 2) res_bisect_t<2>(lam, qh, zhat, xhat, r, n, lane);
+    else if (nel <= 4) res_bisect_t<4>(lam, qh, zhat, xhat, r, n, lane);
+    else res_bisect_t<RES_EPL>(lam, qh, zhat, xhat, r, n, lane);
 }
 
 __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_constant__ PackView P, ResK prm, const double* __restrict__ rhos,
@@ -540,7 +570,7 @@ bool admm_res_plan(const qcqp_pack* p, int runs, ResK* k, size_t* smem_bytes)
     int rpg = (runs + G - 1) / G;
     G = (runs + rpg - 1) / rpg;
     const int nb32 = (v.n + 31) / 32 * 32;
-    if (nb32 > RES_THREADS) return false;
+    if (nb32 > RES_THREADS || v.n > 32 * RES_EPL) return false;
     const int S = RES_THREADS / nb32;
     size_t doubles = (size_t)v.n * (v.n + 1) + 2 * (size_t)v.n + (size_t)rpg * v.n + 5 * (size_t)RES_RB * v.n +
                      (size_t)S * 2 * RES_RB * v.n + 2 * (size_t)v.n + RES_WARPS + 8 + 2 * (size_t)((rpg + v.m - 1) / v.m) + 2;

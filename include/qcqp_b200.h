@@ -191,6 +191,19 @@ int qcqp_sdr_sample_eval(qcqp_pack* pack, const double* mu /*[n]*/, const double
 int qcqp_sdr_sample_eval_device(qcqp_pack* pack, const double* dmu, const double* dF, const double* dZ, uint64_t seed,
                                 int32_t S, double* dX, double* df0, double* dmaxviol, void* stream);
 
+/* ---- Suggest-and-Improve pipeline for S draws in ONE call: SDR randomized rounding (qcqp.py:394-401) -> improve_coord_descent of
+ *      every draw (qcqp.py:181-192) -> best pick in the `better` order (utilities.py:135-146).  What a user of the reference
+ *      writes as `for s in range(S): qcqp.suggest(SDR); qcqp.improve(COORD_DESCENT)`; here the draws never leave the device.
+ *      mu / F == NULL: the factor cached on the pack by the last call that supplied one (the reference caches mu and Sigma on
+ *      self, qcqp.py:394-395).  Z as in qcqp_sdr_sample_eval.  seeds[s]: restart s consumes the stream of
+ *      np.random.seed(seeds[s]) (MT19937 init_genrand, built on the device).  X0 / f0_draw / maxviol_draw (the draws and their
+ *      (f, v)), stats, rng_out (final stream states) and best_idx may be NULL. -------------------------------------------- */
+int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* params, const double* mu /*[n] or NULL*/,
+                         const double* F /*[n][n] or NULL*/, const double* Z /*[S][n] or NULL*/, uint64_t seed, int32_t S,
+                         const uint32_t* seeds /*[S]*/, double* X0 /*[S][n] or NULL*/, double* f0_draw /*[S] or NULL*/,
+                         double* maxviol_draw /*[S] or NULL*/, double* X /*[S][n]*/, double* f0 /*[S]*/, double* maxviol /*[S]*/,
+                         qcqp_cd_stats* stats /*[S] or NULL*/, qcqp_rng_state* rng_out /*[S] or NULL*/, int32_t* best_idx /*or NULL*/);
+
 /* ---- best pick: argmin in the QCQPForm.better order (utilities.py:135-146): lexicographic on
  *      (int(maxviol / tol), f0), later index wins exact ties. ---------------------------------------------------- */
 int qcqp_best(const double* f0, const double* maxviol, int32_t R, double tol, int32_t* best_idx);

@@ -76,6 +76,9 @@ EXPORTS = {
                                        C.c_void_p, C.c_void_p]),
     "qcqp_sdr_sample_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcqp_sdr_cd_pipeline": (C.c_int, [C.c_void_p, C.POINTER(CdParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "qcqp_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "qcqp_best_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

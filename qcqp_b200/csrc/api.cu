@@ -44,6 +44,19 @@ static int check_pack(qcqp_pack* p, const char* who)
 }
 }  // namespace qcqp
 
+// np.random.seed(int): MT19937 init_genrand, pos = 624, no cached gaussian (SURVEY a-7); one thread per stream
+__global__ void mt_seed_kernel(const uint32_t* __restrict__ seeds, qcqp_rng_state* __restrict__ out, int R)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    uint32_t s = seeds[r];
+    for (int i = 0; i < 624; i++) {
+        out[r].key[i] = s;
+        s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+    }
+    out[r].pos = 624; out[r].has_gauss = 0; out[r].gauss = 0.0;
+}
+
 using namespace qcqp;
 
 #define TRY(x) do { int rc__ = (x); if (rc__ != QCQP_OK) return rc__; } while (0)
@@ -200,6 +213,57 @@ extern "C" int qcqp_sdr_sample_eval(qcqp_pack* pack, const double* mu, const dou
     QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, S * n * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF0, S * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, S * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    return QCQP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* params, const double* mu, const double* F, const double* Z,
+                                    uint64_t seed, int32_t S, const uint32_t* seeds, double* X0, double* f0_draw, double* maxviol_draw,
+                                    double* X, double* f0, double* maxviol, qcqp_cd_stats* stats, qcqp_rng_state* rng_out, int32_t* best_idx)
+{
+    TRY(check_pack(pack, "qcqp_sdr_cd_pipeline"));
+    TRY(check_cd_params(params));
+    if (S < 0 || (S > 0 && (!seeds || !X || !f0 || !maxviol))) return fail(QCQP_ERR_INVALID, "qcqp_sdr_cd_pipeline: bad argument");
+    if ((mu == nullptr) != (F == nullptr)) return fail(QCQP_ERR_INVALID, "qcqp_sdr_cd_pipeline: mu and F must be given together");
+    if (!mu && !pack->sdr_ok) return fail(QCQP_ERR_INVALID, "qcqp_sdr_cd_pipeline: no cached SDR factor; pass mu and F once");
+    if (S == 0) return QCQP_OK;
+    const size_t n = pack->v.n;
+    if (mu) {
+        if (!pack->sdr_mu) {
+            QCQP_CUDA_TRY(cudaMalloc((void**)&pack->sdr_mu, n * 8));
+            QCQP_CUDA_TRY(cudaMalloc((void**)&pack->sdr_F, n * n * 8));
+        }
+        QCQP_CUDA_TRY(cudaMemcpyAsync(pack->sdr_mu, mu, n * 8, cudaMemcpyHostToDevice, 0));
+        QCQP_CUDA_TRY(cudaMemcpyAsync(pack->sdr_F, F, n * n * 8, cudaMemcpyHostToDevice, 0));
+        pack->sdr_ok = true;
+    }
+    TRY(ensure_io(pack, 3 * Arena::pad(S * n * 8) + 4 * Arena::pad(S * 8) + Arena::pad(S * sizeof(qcqp_rng_state)) +
+                            Arena::pad(S * sizeof(qcqp_cd_stats)) + Arena::pad(S * 4) + Arena::pad(64)));
+    Arena ar; ar.base = (char*)pack->io;
+    double* dZ = ar.take<double>(S * n * 8); double* dX0 = ar.take<double>(S * n * 8); double* dX = ar.take<double>(S * n * 8);
+    double* dFs = ar.take<double>(S * 8); double* dMs = ar.take<double>(S * 8);
+    double* dF0 = ar.take<double>(S * 8); double* dM = ar.take<double>(S * 8);
+    qcqp_rng_state* dR = ar.take<qcqp_rng_state>(S * sizeof(qcqp_rng_state));
+    qcqp_cd_stats* dS = ar.take<qcqp_cd_stats>(S * sizeof(qcqp_cd_stats));
+    uint32_t* dSeeds = ar.take<uint32_t>(S * 4);
+    int* dBest = ar.take<int>(64);
+    if (Z) QCQP_CUDA_TRY(cudaMemcpyAsync(dZ, Z, S * n * 8, cudaMemcpyHostToDevice, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(dSeeds, seeds, S * 4, cudaMemcpyHostToDevice, 0));
+    mt_seed_kernel<<<(S + 127) / 128, 128, 0, 0>>>(dSeeds, dR, S);
+    QCQP_CUDA_TRY(cudaGetLastError());
+    TRY(sdr_launch(pack, pack->sdr_mu, pack->sdr_F, Z ? dZ : nullptr, seed, S, dX0, dFs, dMs, 0));
+    TRY(cd_launch(pack, params, dX0, S, dR, dX, dF0, dM, dS, 0));
+    if (best_idx) TRY(best_launch(dF0, dM, S, 1e-4, dBest, nullptr, nullptr, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, S * n * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF0, S * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, S * 8, cudaMemcpyDeviceToHost, 0));
+    if (X0) QCQP_CUDA_TRY(cudaMemcpyAsync(X0, dX0, S * n * 8, cudaMemcpyDeviceToHost, 0));
+    if (f0_draw) QCQP_CUDA_TRY(cudaMemcpyAsync(f0_draw, dFs, S * 8, cudaMemcpyDeviceToHost, 0));
+    if (maxviol_draw) QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol_draw, dMs, S * 8, cudaMemcpyDeviceToHost, 0));
+    if (stats) QCQP_CUDA_TRY(cudaMemcpyAsync(stats, dS, S * sizeof(qcqp_cd_stats), cudaMemcpyDeviceToHost, 0));
+    if (rng_out) QCQP_CUDA_TRY(cudaMemcpyAsync(rng_out, dR, S * sizeof(qcqp_rng_state), cudaMemcpyDeviceToHost, 0));
+    if (best_idx) QCQP_CUDA_TRY(cudaMemcpyAsync(best_idx, dBest, 4, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaStreamSynchronize(0));
     return QCQP_OK;
 }

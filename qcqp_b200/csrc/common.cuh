@@ -109,6 +109,10 @@ struct qcqp_pack {
     // scratch of the batched eval / SDR sampler (row-dot partials, device-generated normals)
     void* ws2;
     size_t ws2_bytes;
+    // SDR factor of the last call that supplied one (the reference caches mu / Sigma on self, qcqp.py:394-395)
+    double* sdr_mu;
+    double* sdr_F;
+    bool sdr_ok;
     bool has_eig;
     int objective_dense;
     bool lpc_ok;

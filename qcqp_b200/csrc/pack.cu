@@ -48,6 +48,8 @@ int ensure_workspace2(qcqp_pack* p, size_t bytes)
 {
     if (bytes <= p->ws2_bytes) return QCQP_OK;
     if (p->ws2) cudaFree(p->ws2);
+    if (p->sdr_mu) cudaFree(p->sdr_mu);
+    if (p->sdr_F) cudaFree(p->sdr_F);
     p->ws2 = nullptr;
     p->ws2_bytes = 0;
     size_t want = bytes + bytes / 4;
@@ -108,6 +110,8 @@ extern "C" void qcqp_pack_destroy(qcqp_pack* p)
     if (p->ws) cudaFree(p->ws);
     if (p->io) cudaFree(p->io);
     if (p->ws2) cudaFree(p->ws2);
+    if (p->sdr_mu) cudaFree(p->sdr_mu);
+    if (p->sdr_F) cudaFree(p->sdr_F);
     if (p->ev_ok) for (int i = 0; i < 6; i++) cudaEventDestroy(p->ev[i]);
     delete p;
 }
@@ -269,7 +273,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     qcqp_pack* p = new qcqp_pack();
     std::memset(&p->v, 0, sizeof(p->v));
     std::memset(&p->info, 0, sizeof(p->info));
-    p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->ws2 = nullptr; p->ws2_bytes = 0; p->has_eig = false; p->lpc_ok = false;
+    p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->ws2 = nullptr; p->ws2_bytes = 0; p->has_eig = false; p->lpc_ok = false; p->sdr_mu = nullptr; p->sdr_F = nullptr; p->sdr_ok = false;
     p->ev_ok = false; p->ev_count = 0;
     std::memset(&p->lpc, 0, sizeof(p->lpc));
     cudaGetDevice(&p->device);

@@ -181,6 +181,44 @@ class Pack:
         return X, f0, mv
 
 
+    def sdr_cd_pipeline(self, seeds, mu=None, F=None, Z=None, S=None, seed=0, want_draws=False, want_rng=False, out=None,
+                        num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, strict=False, refresh_every=0):
+        """S draws x_s = mu + z_s F (qcqp.py:394-401), improve_coord_descent of every draw with the stream of
+        np.random.seed(seeds[s]) (qcqp.py:181-192), best pick (utilities.py:135-146) -- one call, the draws stay on the device.
+        mu / F None: the factor cached on the pack by an earlier call.  out: optional preallocated (X, f0, maxviol) arrays
+        (e.g. pinned).  Returns dict(X, f0, maxviol, stats, best[, X0, f0_draw, maxviol_draw][, rng])."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        if Z is not None:
+            Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1, self.n)
+            S = Z.shape[0]
+        S = int(S if S is not None else len(seeds))
+        if len(seeds) != S:
+            raise Exception("need one seed per draw")
+        if mu is not None:
+            mu = np.ascontiguousarray(mu, dtype=np.float64); F = np.ascontiguousarray(F, dtype=np.float64)
+        if out is not None:
+            X, f0, mv = out
+        else:
+            X = np.empty((S, self.n)); f0 = np.empty(S); mv = np.empty(S)
+        stats = (CdStats * S)()
+        X0 = np.empty((S, self.n)) if want_draws else None
+        fd = np.empty(S) if want_draws else None; vd = np.empty(S) if want_draws else None
+        rng = (RngState * S)() if want_rng else None
+        bi = C.c_int32(-1)
+        prm = CdParams(int(num_iters), float(viol_tol), float(tol), int(bool(phase1)), int(strict), int(refresh_every))
+        check(_lib.load().qcqp_sdr_cd_pipeline(
+            self._h, C.byref(prm), _ptr(mu) if mu is not None else None, _ptr(F) if mu is not None else None,
+            _ptr(Z) if Z is not None else None, int(seed), S, _ptr(seeds), _ptr(X0) if want_draws else None,
+            _ptr(fd) if want_draws else None, _ptr(vd) if want_draws else None, _ptr(X), _ptr(f0), _ptr(mv),
+            C.cast(stats, C.c_void_p), C.cast(rng, C.c_void_p) if want_rng else None, C.cast(C.byref(bi), C.c_void_p)))
+        res = dict(X=X, f0=f0, maxviol=mv, stats=stats, best=int(bi.value))
+        if want_draws:
+            res.update(X0=X0, f0_draw=fd, maxviol_draw=vd)
+        if want_rng:
+            res["rng"] = rng
+        return res
+
+
 def best(f0, maxviol, tol=1e-4):
     """Index of the best point in QCQPForm.better order (utilities.py:135-146)."""
     f0 = np.ascontiguousarray(f0, dtype=np.float64).ravel(); mv = np.ascontiguousarray(maxviol, dtype=np.float64).ravel()

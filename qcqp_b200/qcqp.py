@@ -104,6 +104,7 @@ class QCQP:
         self.sdr_sol = X
         self.sdr_bound = None if bound is None else (-bound if self.maximize_flag else bound)
         self.mu = None
+        self._factor_on_device = False
 
     # ---- suggest (qcqp.py:378-401) -----------------------------------------------------------------------
     def suggest(self, method=s.RANDOM, eps=1e-8, *args, **kwargs):
@@ -144,6 +145,33 @@ class QCQP:
             Z = np.stack([np.random.standard_normal(self.n) for _ in range(S)])
             X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=Z)
         return self._assign(X, f0, mv)
+
+    def suggest_improve(self, samples=1, seed=0, eps=1e-8, device_rng=False, corrected=False, **kwargs):
+        """Batch form of the README loop `qcqp.suggest(SDR); qcqp.improve(COORD_DESCENT)` for `samples` draws in ONE engine call
+        (qcqp_sdr_cd_pipeline): the draws stay on the device, restart s consumes the stream of np.random.seed(seed + s), the
+        best point in the `better` order is written back.  kwargs: improve_coord_descent's (num_iters, viol_tol, tol, phase1)."""
+        S = int(samples)
+        if self.sdr_sol is None:
+            self.sdr_sol, self.sdr_bound = relax.solve_sdr(self.qcqp_form)
+            if self.maximize_flag:
+                self.sdr_bound *= -1
+        fresh = self.mu is None
+        if fresh:
+            self.mu, self.Sigma, self._F = engine.sdr_factor(self.sdr_sol, eps=eps, corrected=corrected)
+        fresh = fresh or not getattr(self, "_factor_on_device", False)
+        Z = None if device_rng else np.stack([np.random.standard_normal(self.n) for _ in range(S)])
+        seeds = [(int(seed) + r) % (2 ** 32) for r in range(S)]
+        kw = dict(num_iters=kwargs.get('num_iters', 1000), viol_tol=kwargs.get('viol_tol', 1e-2), tol=kwargs.get('tol', 1e-4),
+                  phase1=kwargs.get('phase1', True), strict=kwargs.get('strict', False))
+        res = self._pack.sdr_cd_pipeline(seeds, mu=self.mu if fresh else None, F=self._F if fresh else None, Z=Z, S=S, seed=int(seed), **kw)
+        self._factor_on_device = True
+        for r in range(S):
+            if res["stats"][r].status == 1:
+                raise ValueError("max() arg is an empty sequence")          # qcqp.py:117
+            if res["stats"][r].status == 2:
+                raise OverflowError("Range exceeds valid bounds")           # utilities.py:267
+        self.cd_stats = res["stats"]
+        return self._assign(res["X"], res["f0"], res["maxviol"])
 
     # ---- improve (qcqp.py:403-432) -----------------------------------------------------------------------
     def _improve(self, method, *args, **kwargs):

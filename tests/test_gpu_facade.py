@@ -105,3 +105,49 @@ def test_suggest_sdr_and_spectral_with_the_host_relaxation():
     qm.suggest(Q.SDR, samples=32)
     f, v = qm.improve(Q.COORD_DESCENT, seed=3, num_iters=50)
     assert f <= qm.sdr_bound + 1e-3 and v < 1e-2      # SDR-based upper bound on the cut
+
+
+def test_sdr_cd_pipeline_equals_separate_calls():
+    """qcqp_sdr_cd_pipeline (draws stay on the device, MT19937 streams seeded on the device, cached SDR factor) returns
+    bit for bit what qcqp_sdr_sample_eval -> qcqp_cd_improve -> qcqp_best return through host buffers."""
+    from qcqp_b200 import engine, problems as pb
+    n, S = 48, 40
+    forms, _ = pb.boolean_least_squares(n, 70, seed=3)
+    pack = engine.Pack(forms)
+    mu, _Sg, F = engine.sdr_factor(pb.synthetic_sdr_solution(n, rank=5, seed=2))
+    Z = np.random.RandomState(8).standard_normal((S, n))
+    seeds = 77 + 3 * np.arange(S)
+    X0, fs, vs = pack.sdr_sample_eval(mu, F, Z=Z)
+    rng = engine.rng_states(seeds=seeds)
+    X, f0, mv, st = pack.cd_improve(X0, rng)
+    res = pack.sdr_cd_pipeline(seeds, mu=mu, F=F, Z=Z, want_draws=True, want_rng=True)
+    assert np.array_equal(res["X0"], X0) and np.array_equal(res["f0_draw"], fs) and np.array_equal(res["maxviol_draw"], vs)
+    assert np.array_equal(res["X"], X) and np.array_equal(res["f0"], f0) and np.array_equal(res["maxviol"], mv)
+    assert res["best"] == engine.best(f0, mv)
+    for s in range(S):
+        assert bytes(res["rng"][s]) == bytes(rng[s])                         # device init_genrand == np.random.seed
+        assert (res["stats"][s].steps_p1, res["stats"][s].steps_p2) == (st[s].steps_p1, st[s].steps_p2)
+    res2 = pack.sdr_cd_pipeline(seeds, Z=Z)                                  # cached factor
+    assert np.array_equal(res2["X"], X)
+    pack2 = engine.Pack(forms)
+    with pytest.raises(Exception):
+        pack2.sdr_cd_pipeline(seeds, Z=Z)                                    # nothing cached yet
+    pack.close(); pack2.close()
+
+
+def test_facade_suggest_improve_batch_equals_two_step_flow():
+    """QCQP.suggest_improve(samples=S, seed=s) == suggest(SDR, samples=S) followed by improve(COORD_DESCENT, seed=s)."""
+    from qcqp_b200 import QCQP, COORD_DESCENT, SDR, problems as pb
+    n, S = 30, 12
+    forms, _ = pb.boolean_least_squares(n, 45, seed=4)
+    Xs = pb.synthetic_sdr_solution(n, rank=4, seed=1)
+    a = QCQP(forms); a.set_sdr_solution(Xs)
+    b = QCQP(forms); b.set_sdr_solution(Xs)
+    np.random.seed(5)
+    a.suggest(SDR, samples=S)
+    fa, va = a.improve(COORD_DESCENT, seed=900)
+    np.random.seed(5)
+    fb, vb = b.suggest_improve(samples=S, seed=900)
+    assert fa == fb and va == vb and np.array_equal(a.X, b.X) and a.best_index == b.best_index
+    fb2, vb2 = b.suggest_improve(samples=S, seed=901)          # second call: factor already on the device
+    assert np.isfinite(fb2) and vb2 < 1e-2

@@ -48,8 +48,6 @@ int ensure_workspace2(qcqp_pack* p, size_t bytes)
 {
     if (bytes <= p->ws2_bytes) return QCQP_OK;
     if (p->ws2) cudaFree(p->ws2);
-    if (p->sdr_mu) cudaFree(p->sdr_mu);
-    if (p->sdr_F) cudaFree(p->sdr_F);
     p->ws2 = nullptr;
     p->ws2_bytes = 0;
     size_t want = bytes + bytes / 4;

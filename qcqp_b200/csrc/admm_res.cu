@@ -27,7 +27,9 @@ constexpr int RES_THREADS = 512;
 constexpr int RES_WARPS = RES_THREADS / 32;
 constexpr int RES_RB = 4;   // runs per GEMM batch (2 * RES_RB accumulators per thread)
 
-enum { CMD_IDLE = 0, CMD_STEP = 1, CMD_RESET_STEP = 2 };
+// command word of a run, written by its home CTA: where this iteration's z is (home-written z at phase starts -- u is reset then --
+// or the z rows all CTAs of the group computed during the previous S2) and which phase the run is in
+enum { CMD_IDLE = 0, CMD_HOME_P1 = 1, CMD_HOME_P2 = 2, CMD_SPEC_P1 = 3, CMD_SPEC_P2 = 4 };
 
 struct ResK {
     int num_iters;
@@ -39,7 +41,8 @@ struct ResK {
 
 // per-run block in the workspace (doubles unless noted): see res_run_doubles()
 struct RunView {
-    double* z;        // [n]   current z (input of S1)
+    double* z;        // [n]   z written by the home CTA (phase starts)
+    double* zs;       // [2][n] z rows computed by all CTAs of the group, by step parity
     double* d;        // [m][n] x_i - u_i
     double* viol;     // [m]   violation of z for constraint i
     double* x0;       // [n]
@@ -49,12 +52,12 @@ struct RunView {
     double* sc;       // [8] scalars: f_x0, mv_x0, f_x1, mv_x1, f_best, mv_best
     int* ic;          // [8] ints: cmd, phase, t, have_last, iters_p1, iters_p2, calls_lo, calls_hi
 };
-__host__ __device__ inline size_t res_run_doubles(int n, int m) { return (size_t)n * (5 + m) + m + 8 + 4; }
+__host__ __device__ inline size_t res_run_doubles(int n, int m) { return (size_t)n * (7 + m) + m + 8 + 4; }
 __device__ __forceinline__ RunView res_run_view(double* ws, int run, int n, int m)
 {
     RunView v;
     double* b = ws + (size_t)run * res_run_doubles(n, m);
-    v.z = b; v.d = v.z + n; v.viol = v.d + (size_t)m * n; v.x0 = v.viol + m; v.x1 = v.x0 + n; v.bestx = v.x1 + n; v.last_z = v.bestx + n;
+    v.z = b; v.zs = v.z + n; v.d = v.zs + 2 * n; v.viol = v.d + (size_t)m * n; v.x0 = v.viol + m; v.x1 = v.x0 + n; v.bestx = v.x1 + n; v.last_z = v.bestx + n;
     v.sc = v.last_z + n; v.ic = reinterpret_cast<int*>(v.sc + 8);
     return v;
 }
@@ -125,6 +128,8 @@ struct ResSmem {
     double* vh;     // [RB][n]   Q^T v
     double* xh;     // [RB][n]   xhat(nu)
     double* part;   // [S][2 RB][n] partial sums of the GEMM passes; also scratch of the home stage (rhs, z, red)
+    double* q0s;    // [n] q_0 dense
+    int* cmds;      // [rpg] command of every run of my group, as read in S1 of this step
     double* hs;     // [2 * homes] f0(z) and |z - last_z|^2 of the runs this CTA is home of (S1 -> S2)
     int* flag;      // [RB] early-out / command
 };
@@ -156,40 +161,75 @@ __device__ __forceinline__ void res_bisect_t(const double* lam, const double* qh
     // is taken with a reciprocal refined to full precision (1-2 ulp) instead of the 125-cycle IEEE division (straight-line code:
     // the NEL quotients overlap), and the two sums share one shuffle reduction.  A denominator outside the reciprocal's safe
     // range sends the whole warp through the exact division.  The returned xhat((s+e)/2) below always uses the exact division.
-    auto phi = [&](double nu) {
+    double L2x[NEL];
+#pragma unroll
+    for (int u = 0; u < NEL; u++) L2x[u] = 2 * L[u];
+    // xhat = -(nu qhat - 2 zhat) / (2 + nu 2 lambda) through the refined reciprocal: 9 FP64 instructions per component
+    auto quot = [&](double nu, int u) {
+        const double num = fma(nu, Qh[u], -Z2[u]), den = fma(nu, L2x[u], 2.0);
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+        double e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
+        e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
+        return -(num * y);
+    };
+    auto exact_sum = [&](double nu) {
         double acc = 0.0;
-        bool odd = false;
 #pragma unroll
         for (int u = 0; u < NEL; u++) {
-            const double num = nu * Qh[u] - Z2[u], den = 2 * (1 + nu * L[u]);
-            const double ad = fabs(den);
-            odd = odd || !(ad > 1e-280 && ad < 1e280);
-            double y;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
-            double e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
-            e1 = fma(-den, y, 1.0); y = fma(y, e1, y);
-            const double xh = -(num * y);
+            const double xh = -((nu * Qh[u] - Z2[u]) / (2 * (1 + nu * L[u])));
             acc = fma(fma(L[u], xh, Qh[u]), xh, acc);
         }
-        if (__any_sync(FULL, odd)) {
-            acc = 0.0;
+        return acc;
+    };
+    // a denominator outside the reciprocal's range (zero, denormal, overflow) shows up as a non-finite sum: redo exactly
+    auto phi = [&](double nu) {
+        double acc = 0.0;
 #pragma unroll
-            for (int u = 0; u < NEL; u++) {
-                const double xh = -((nu * Qh[u] - Z2[u]) / (2 * (1 + nu * L[u])));
-                acc = fma(fma(L[u], xh, Qh[u]), xh, acc);
-            }
+        for (int u = 0; u < NEL; u++) { const double xh = quot(nu, u); acc = fma(fma(L[u], xh, Qh[u]), xh, acc); }
+        acc = warp_sum(acc);
+        if (!(fabs(acc) < QCQP_INF)) acc = warp_sum(exact_sum(nu));
+        return acc + r;
+    };
+    // three multipliers at once (one bisection step and both of its possible successors): the 3 NEL quotient chains and the
+    // three shuffle reductions overlap, so two levels of the search cost little more than one
+    auto phi3 = [&](double nu0, double nu1, double nu2, double& o0, double& o1, double& o2) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int u = 0; u < NEL; u++) {
+            const double x0 = quot(nu0, u), x1 = quot(nu1, u), x2 = quot(nu2, u);
+            a0 = fma(fma(L[u], x0, Qh[u]), x0, a0);
+            a1 = fma(fma(L[u], x1, Qh[u]), x1, a1);
+            a2 = fma(fma(L[u], x2, Qh[u]), x2, a2);
         }
-        return warp_sum(acc) + r;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(FULL, a0, o); a1 += __shfl_xor_sync(FULL, a1, o); a2 += __shfl_xor_sync(FULL, a2, o);
+        }
+        if (!(fabs(a0) < QCQP_INF) || !(fabs(a1) < QCQP_INF) || !(fabs(a2) < QCQP_INF)) {
+            a0 = warp_sum(exact_sum(nu0)); a1 = warp_sum(exact_sum(nu1)); a2 = warp_sum(exact_sum(nu2));
+        }
+        o0 = a0 + r; o1 = a1 + r; o2 = a2 + r;
     };
     int guard = 0;
     if (s == -QCQP_INF) { s = -1.; while (phi(s) <= 0 && ++guard < 4096) s *= 2.; }
     if (e == QCQP_INF) { e = 1.; while (phi(e) >= 0 && ++guard < 8192) e *= 2.; }
     while (e - s > 1e-6) {
-        double mid = (s + e) / 2.;
-        double ph = phi(mid);
+        // the reference's loop (utilities.py:187-195), two iterations per pass: mid, then (s+mid)/2 or (mid+e)/2 -- the same
+        // expressions the sequential loop would evaluate next, so the decisions are identical
+        const double mid = (s + e) / 2.;
+        const double midl = (s + mid) / 2., midr = (mid + e) / 2.;
+        double ph, phl, phr;
+        phi3(mid, midl, midr, ph, phl, phr);
         if (ph > 0) s = mid;
         else if (ph < 0) e = mid;
         else { s = e = mid; break; }
+        if (!(e - s > 1e-6)) break;
+        const double ph2 = (ph > 0) ? phr : phl;
+        const double mid2 = (s + e) / 2.;
+        if (ph2 > 0) s = mid2;
+        else if (ph2 < 0) e = mid2;
+        else { s = e = mid2; break; }
     }
     const double nu = (s + e) / 2.;
     for (int t = lane; t < n; t += 32) xhat[t] = -((nu * qh[t] - 2 * zhat[t]) / (2 * (1 + nu * lam[t])));
@@ -233,6 +273,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
         sm.xh = p; p += RES_RB * n;
         sm.part = p; p += (size_t)S * 2 * RES_RB * n + 2 * n + RES_WARPS + 8;
         sm.hs = p; p += 2 * ((prm.rpg + m - 1) / m) + 2;
+        sm.q0s = p; p += n;
+        sm.cmds = reinterpret_cast<int*>(p); p += (prm.rpg + 1) / 2 + 1;
         sm.flag = reinterpret_cast<int*>(p);
     }
     unsigned* bar = bars + g;
@@ -247,6 +289,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
         for (int e = tid; e < n * n; e += RES_THREADS) { const int a = e / n, b = e - a * n; sm.Q[a * ldq + b] = Qg[e]; }
         for (int t = tid; t < n; t += RES_THREADS) { sm.lam[t] = P.eig_lambda[(size_t)ci * n + t]; sm.qh[t] = P.eig_qhat[(size_t)ci * n + t]; }
         for (int t = tid; t < prm.rpg * n; t += RES_THREADS) sm.u[t] = 0.0;
+        for (int t = tid; t < n; t += RES_THREADS) sm.q0s[t] = 0.0;
+        __syncthreads();
+        for (long long e = P.q_ptr[0] + tid; e < P.q_ptr[1]; e += RES_THREADS) sm.q0s[P.q_idx[e]] = P.q_val[e];
     }
     __syncthreads();
 
@@ -339,7 +384,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
         if (tid == 0) { rv.sc[4] = rv.sc[2]; rv.sc[5] = rv.sc[3]; rv.ic[1] = 2; rv.ic[2] = 0; rv.ic[3] = 0; }
         __syncthreads();
         if (prm.num_iters <= 0) { finish_run(rv, run); return; }
-        if (tid == 0) { rv.ic[2] = 1; rv.ic[5] = 1; rv.ic[0] = CMD_RESET_STEP; }
+        if (tid == 0) { rv.ic[2] = 1; rv.ic[5] = 1; rv.ic[0] = CMD_HOME_P2; }
         next_z(rv, run, 2, true, rv.x1);
     };
 
@@ -358,7 +403,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
         }
         __syncthreads();
         if (prm.phase1 && prm.num_iters > 0 && !(mv < prm.tol)) {
-            if (tid == 0) { rv.ic[1] = 1; rv.ic[2] = 1; rv.ic[4] = 1; rv.ic[0] = CMD_RESET_STEP; }
+            if (tid == 0) { rv.ic[1] = 1; rv.ic[2] = 1; rv.ic[4] = 1; rv.ic[0] = CMD_HOME_P1; }
             next_z(rv, run, 1, true, rv.x0);
         } else {
             enter_phase2(rv, run);   // x1 = better(x0, z = x0) is x0 itself
@@ -367,6 +412,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
     bar_target += m;
     group_barrier(bar, bar_target);
 
+    int par = 0;   // step parity: S1 reads zs[par], S2 writes zs[par ^ 1]
     for (;;) {
         // =========================== S1: my constraint, every active run of my group ===========================
         int any_active = 0;
@@ -377,6 +423,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                 int cmd = CMD_IDLE;
                 if (tid < nb) cmd = __ldcg(res_run_view(ws, run0 + b0 + tid, n, m).ic);
                 sm.flag[tid] = cmd;
+                if (tid < nb) sm.cmds[b0 + tid] = cmd;
             }
             __syncthreads();
             int act = 0;
@@ -387,8 +434,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                 const int q = e / n, a = e - q * n;
                 double zv = 0.0, uv = 0.0;
                 if ((act >> q) & 1) {
-                    zv = __ldcg(res_run_view(ws, run0 + b0 + q, n, m).z + a);
-                    if (sm.flag[q] == CMD_RESET_STEP) sm.u[(size_t)(b0 + q) * n + a] = 0.0;
+                    const RunView rq = res_run_view(ws, run0 + b0 + q, n, m);
+                    const bool home_z = (sm.flag[q] == CMD_HOME_P1 || sm.flag[q] == CMD_HOME_P2);
+                    zv = __ldcg((home_z ? rq.z : rq.zs + (size_t)par * n) + a);
+                    if (home_z) sm.u[(size_t)(b0 + q) * n + a] = 0.0;   // xs = [x_init] * m, us = 0 at a phase start
                     uv = sm.u[(size_t)(b0 + q) * n + a];
                 }
                 sm.zs[e] = zv; sm.vs[e] = zv + uv;
@@ -500,13 +549,69 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
         bar_target += m;
         group_barrier(bar, bar_target);
 
-        // =========================== S2: loop control of the runs I am home of ===========================
+        // =========================== S2 ===========================
+        // (a) every CTA of the group: the next z of every active run under the assumption that the run goes on in its phase.
+        //     D = sum_i d_i in full by every CTA (a few overlapped L2 round trips, no extra barrier), then only MY rows
+        //     (a = ci, ci + m, ...) of z = D/m or Zinv (2 rho D - q0), written to the other parity's buffer
+        for (int b0 = 0; b0 < nrun; b0 += RES_RB) {
+            const int nb = (nrun - b0 < RES_RB) ? (nrun - b0) : RES_RB;
+            int act = 0;
+            for (int q = 0; q < nb; q++) act |= (sm.cmds[b0 + q] != CMD_IDLE) << q;
+            if (act == 0) continue;
+            double* rhs = sm.part;   // [RB][n]
+            {
+                const int slice = tid / nb32, a = tid - slice * nb32;
+                for (int q = slice; q < nb; q += S) {
+                    if (a < n && ((act >> q) & 1)) {
+                        const int run = run0 + b0 + q;
+                        const double* dq = res_run_view(ws, run, n, m).d + a;
+                        double D = 0.0;
+                        int i = 0;
+                        for (; i + 8 <= m; i += 8) {
+                            double dv[8];
+#pragma unroll
+                            for (int u8 = 0; u8 < 8; u8++) dv[u8] = __ldcg(dq + (size_t)(i + u8) * n);
+#pragma unroll
+                            for (int u8 = 0; u8 < 8; u8++) D = D + dv[u8];
+                        }
+                        for (; i < m; i++) D = D + __ldcg(dq + (size_t)i * n);
+                        const int cmd = sm.cmds[b0 + q];
+                        const bool p2 = (cmd == CMD_HOME_P2 || cmd == CMD_SPEC_P2);
+                        rhs[q * n + a] = p2 ? (2 * rhos[run / prm.R] * D - sm.q0s[a]) : D;
+                    }
+                }
+            }
+            __syncthreads();
+            if (ci < n) {
+                const int nrows = (n - ci + m - 1) / m;
+                for (int idx = warp; idx < nb * nrows; idx += RES_WARPS) {
+                    const int q = idx / nrows, a = ci + (idx - q * nrows) * m;
+                    if (!((act >> q) & 1)) continue;
+                    const int run = run0 + b0 + q;
+                    const int cmd = sm.cmds[b0 + q];
+                    double* zo = res_run_view(ws, run, n, m).zs + (size_t)(par ^ 1) * n;
+                    if (cmd == CMD_HOME_P2 || cmd == CMD_SPEC_P2) {
+                        const double* Za = Zinv + ((size_t)(run / prm.R) * n + a) * n;
+                        double acc = 0.0;
+                        for (int bb = lane; bb < n; bb += 32) acc = fma(Za[bb], rhs[q * n + bb], acc);
+                        acc = warp_sum(acc);
+                        if (lane == 0) zo[a] = acc;
+                    } else if (lane == 0) {
+                        zo[a] = rhs[q * n + a] / m;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // (b) the runs I am home of: the reference's loop control on this iteration's z; a run that goes on in its phase takes the
+        //     rows computed in (a), a phase start gets its z from the home CTA
         for (int lr = ci; lr < nrun; lr += m) {
             const int run = run0 + lr;
             const RunView rv = res_run_view(ws, run, n, m);
-            if (rv.ic[0] == CMD_IDLE) continue;
+            const int cmd = sm.cmds[lr];
+            if (cmd == CMD_IDLE) continue;
             const int phase = rv.ic[1], t = rv.ic[2];
-            // this iteration's z: objective and step length from S1's side warps, max violation from the m CTAs (rotated forms)
+            // objective and step length from S1's side warps, max violation from the m CTAs (rotated forms)
             double fz = sm.hs[2 * (lr / m)], mvz = -QCQP_INF;
             const double step2 = sm.hs[2 * (lr / m) + 1];
             if (warp == 0) {
@@ -517,28 +622,27 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
             __syncthreads();
             mvz = h_red[1];
             __syncthreads();
-            const double* h_z = rv.z;
+            const double* zt = (cmd == CMD_HOME_P1 || cmd == CMD_HOME_P2) ? rv.z : rv.zs + (size_t)par * n;   // this iteration's z
             if (phase == 1) {
                 if (t >= prm.num_iters || mvz < prm.tol) {
                     // x1 = better(x0, z) (qcqp.py:280-281)
                     if (!res_better_first(rv.sc[1], rv.sc[0], mvz, fz)) {
-                        for (int a = tid; a < n; a += RES_THREADS) rv.x1[a] = h_z[a];
+                        for (int a = tid; a < n; a += RES_THREADS) rv.x1[a] = __ldcg(zt + a);
                         if (tid == 0) { rv.sc[2] = fz; rv.sc[3] = mvz; }
                     }
                     __syncthreads();
                     enter_phase2(rv, run);
-                } else {
-                    if (tid == 0) { rv.ic[2] = t + 1; rv.ic[4] = rv.ic[4] + 1; rv.ic[0] = CMD_STEP; }
-                    next_z(rv, run, 1, false, nullptr);
+                } else if (tid == 0) {
+                    rv.ic[2] = t + 1; rv.ic[4] = rv.ic[4] + 1; rv.ic[0] = CMD_SPEC_P1;
                 }
             } else {
                 bool stop = false;
                 if (rv.ic[3] && sqrt(step2) < prm.tol) stop = true;
                 if (!stop) {
-                    for (int a = tid; a < n; a += RES_THREADS) rv.last_z[a] = h_z[a];
+                    for (int a = tid; a < n; a += RES_THREADS) rv.last_z[a] = __ldcg(zt + a);
                     if (mvz > prm.viol_lim) stop = true;
                     else if (res_better_first(mvz, fz, rv.sc[5], rv.sc[4])) {
-                        for (int a = tid; a < n; a += RES_THREADS) rv.bestx[a] = h_z[a];
+                        for (int a = tid; a < n; a += RES_THREADS) rv.bestx[a] = __ldcg(zt + a);
                         __syncthreads();
                         if (tid == 0) { rv.sc[4] = fz; rv.sc[5] = mvz; }
                     }
@@ -546,13 +650,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                 }
                 __syncthreads();
                 if (stop) finish_run(rv, run);
-                else {
-                    if (tid == 0) { rv.ic[3] = 1; rv.ic[2] = t + 1; rv.ic[5] = rv.ic[5] + 1; rv.ic[0] = CMD_STEP; }
-                    next_z(rv, run, 2, false, nullptr);
-                }
+                else if (tid == 0) { rv.ic[3] = 1; rv.ic[2] = t + 1; rv.ic[5] = rv.ic[5] + 1; rv.ic[0] = CMD_SPEC_P2; }
             }
             __syncthreads();
         }
+        par ^= 1;
         bar_target += m;
         group_barrier(bar, bar_target);
     }
@@ -573,7 +675,7 @@ bool admm_res_plan(const qcqp_pack* p, int runs, ResK* k, size_t* smem_bytes)
     if (nb32 > RES_THREADS || v.n > 32 * RES_EPL) return false;
     const int S = RES_THREADS / nb32;
     size_t doubles = (size_t)v.n * (v.n + 1) + 2 * (size_t)v.n + (size_t)rpg * v.n + 5 * (size_t)RES_RB * v.n +
-                     (size_t)S * 2 * RES_RB * v.n + 2 * (size_t)v.n + RES_WARPS + 8 + 2 * (size_t)((rpg + v.m - 1) / v.m) + 2;
+                     (size_t)S * 2 * RES_RB * v.n + 2 * (size_t)v.n + RES_WARPS + 8 + 2 * (size_t)((rpg + v.m - 1) / v.m) + 2 + (size_t)v.n + (size_t)(rpg + 1) / 2 + 1;
     size_t bytes = doubles * 8 + 64;
     if (bytes > (size_t)max_smem_optin(p->device)) return false;
     k->G = G; k->rpg = rpg; k->S = S; k->nb32 = nb32; k->runs = runs;

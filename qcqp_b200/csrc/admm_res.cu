@@ -37,6 +37,8 @@ struct ResK {
     int phase1;
     int K, R, runs, G, rpg;   // rpg: runs per group
     int S, nb32;              // a-slices of the GEMM passes, n rounded up to a multiple of 32
+    int ldq;                  // row stride of the resident Q_i: n + 1 (FMA passes) or = 4 mod 16 (DMMA fragments conflict-free)
+    int no_mma;               // QCQP_ADMM_NO_MMA=1: FMA-pipe GEMM passes even when n is a multiple of 8 (A/B runs)
 };
 
 // per-run block in the workspace (doubles unless noted): see res_run_doubles()
@@ -126,7 +128,8 @@ struct ResSmem {
     double* vs;     // [RB][n]   z + u
     double* zh;     // [RB][n]   Q^T z
     double* vh;     // [RB][n]   Q^T v
-    double* xh;     // [RB][n]   xhat(nu)
+    double* xh;     // [RB][n]   xhat(nu)   (DMMA passes: [n][RB], run-interleaved)
+    double* zvT;    // [n][2 RB] (z_0, v_0, .., z_3, v_3) per component: B fragments of the first DMMA pass
     double* part;   // [S][2 RB][n] partial sums of the GEMM passes; also scratch of the home stage (rhs, z, red)
     double* q0s;    // [n] q_0 dense
     int* cmds;      // [rpg] command of every run of my group, as read in S1 of this step
@@ -134,12 +137,19 @@ struct ResSmem {
     int* flag;      // [RB] early-out / command
 };
 
+// D(8x8) += A(8x4, row) * B(4x8, col) in FP64 on the tensor pipe (DMMA).  Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// c0/c1 = C[lane/4][2 (lane%4) + {0,1}].  The only dense contraction of this kernel -- the two passes over the resident Q_i.
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // the multiplier search of onecons_qcqp (utilities.py:168-195) by one warp; zhat = Q^T v, result xhat.
 // A lane keeps its (at most RES_EPL) eigen-components in registers for the ~65 evaluations of phi.
 constexpr int RES_EPL = 6;   // n <= 192 (shared memory holds Q_i up to n ~ 165)
 
 template <int NEL>
-__device__ __forceinline__ void res_bisect_t(const double* lam, const double* qh, const double* zhat, double* xhat, double r, int n, int lane)
+__device__ __forceinline__ void res_bisect_t(const double* lam, const double* qh, const double* zhat, double* xhat, int xstride, double r, int n, int lane)
 {
     double L[NEL], Qh[NEL], Z2[NEL];
 #pragma unroll
@@ -232,16 +242,16 @@ __device__ __forceinline__ void res_bisect_t(const double* lam, const double* qh
         else { s = e = mid2; break; }
     }
     const double nu = (s + e) / 2.;
-    for (int t = lane; t < n; t += 32) xhat[t] = -((nu * qh[t] - 2 * zhat[t]) / (2 * (1 + nu * lam[t])));
+    for (int t = lane; t < n; t += 32) xhat[(size_t)t * xstride] = -((nu * qh[t] - 2 * zhat[t]) / (2 * (1 + nu * lam[t])));
 }
 
-__device__ __forceinline__ void res_bisect(const double* lam, const double* qh, const double* zhat, double* xhat, double r, int n, int lane)
+__device__ __forceinline__ void res_bisect(const double* lam, const double* qh, const double* zhat, double* xhat, int xstride, double r, int n, int lane)
 {
     const int nel = (n + 31) >> 5;
-    if (nel <= 1) res_bisect_t<1>(lam, qh, zhat, xhat, r, n, lane);
-    else if (nel == 2) res_bisect_t<2>(lam, qh, zhat, xhat, r, n, lane);
-    else if (nel <= 4) res_bisect_t<4>(lam, qh, zhat, xhat, r, n, lane);
-    else res_bisect_t<RES_EPL>(lam, qh, zhat, xhat, r, n, lane);
+    if (nel <= 1) res_bisect_t<1>(lam, qh, zhat, xhat, xstride, r, n, lane);
+    else if (nel == 2) res_bisect_t<2>(lam, qh, zhat, xhat, xstride, r, n, lane);
+    else if (nel <= 4) res_bisect_t<4>(lam, qh, zhat, xhat, xstride, r, n, lane);
+    else res_bisect_t<RES_EPL>(lam, qh, zhat, xhat, xstride, r, n, lane);
 }
 
 __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_constant__ PackView P, ResK prm, const double* __restrict__ rhos,
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, m = P.m;
-    const int ldq = n + 1;
+    const int ldq = prm.ldq;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ci = blockIdx.x % m;          // my constraint (0-based)
     const int g = blockIdx.x / m;           // my run group
@@ -271,6 +281,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
         sm.zh = p; p += RES_RB * n;
         sm.vh = p; p += RES_RB * n;
         sm.xh = p; p += RES_RB * n;
+        sm.zvT = p; p += 2 * RES_RB * n;
         sm.part = p; p += (size_t)S * 2 * RES_RB * n + 2 * n + RES_WARPS + 8;
         sm.hs = p; p += 2 * ((prm.rpg + m - 1) / m) + 2;
         sm.q0s = p; p += n;
@@ -412,6 +423,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
     bar_target += m;
     group_barrier(bar, bar_target);
 
+    const bool use_mma = (n & 7) == 0 && !prm.no_mma;
     int par = 0;   // step parity: S1 reads zs[par], S2 writes zs[par ^ 1]
     for (;;) {
         // =========================== S1: my constraint, every active run of my group ===========================
@@ -441,10 +453,28 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                     uv = sm.u[(size_t)(b0 + q) * n + a];
                 }
                 sm.zs[e] = zv; sm.vs[e] = zv + uv;
+                if (use_mma) { sm.zvT[a * (2 * RES_RB) + 2 * q] = zv; sm.zvT[a * (2 * RES_RB) + 2 * q + 1] = zv + uv; }
             }
             __syncthreads();
-            // B: [zhat, vhat] = Q^T [z, v]: thread (slice, b) walks its slice of a for the whole batch
-            {
+            // B: [zhat, vhat] = Q^T [z, v] for the whole batch.  n a multiple of 8: FP64 tensor-core tiles -- a warp owns 8 outputs b,
+            //    the 8 columns are (z_0, v_0, .., z_3, v_3), k walks a in steps of 4.  Otherwise: thread (slice, b) walks its slice of a.
+            if (use_mma) {
+                const int gq = lane >> 2, tq = lane & 3;
+                for (int mt = warp; mt < (n >> 3); mt += RES_WARPS) {
+                    const int bb0 = mt << 3;
+                    // four independent accumulator chains (k = a0, a0 + 4, a0 + 8, a0 + 12): the DMMA latency overlaps
+                    double c0[4] = {0.0, 0.0, 0.0, 0.0}, c1[4] = {0.0, 0.0, 0.0, 0.0};
+                    int a0 = 0;
+                    for (; a0 + 16 <= n; a0 += 16) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            dmma_m8n8k4(c0[u], c1[u], sm.Q[(a0 + 4 * u + tq) * ldq + bb0 + gq], sm.zvT[(a0 + 4 * u + tq) * (2 * RES_RB) + gq]);
+                    }
+                    for (; a0 < n; a0 += 4) dmma_m8n8k4(c0[0], c1[0], sm.Q[(a0 + tq) * ldq + bb0 + gq], sm.zvT[(a0 + tq) * (2 * RES_RB) + gq]);
+                    sm.zh[tq * n + bb0 + gq] = (c0[0] + c0[1]) + (c0[2] + c0[3]);
+                    sm.vh[tq * n + bb0 + gq] = (c1[0] + c1[1]) + (c1[2] + c1[3]);
+                }
+            } else {
                 const int slice = tid / nb32, b = tid - slice * nb32;
                 double acc[2 * RES_RB];
 #pragma unroll
@@ -464,13 +494,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                 }
             }
             __syncthreads();
-            for (int e = tid; e < 2 * RES_RB * n; e += RES_THREADS) {
-                const int q = e / n, b = e - q * n;
-                double s = 0.0;
-                for (int sl = 0; sl < S; sl++) s += sm.part[((size_t)sl * 2 * RES_RB + q) * n + b];
-                if (q & 1) sm.vh[(q >> 1) * n + b] = s; else sm.zh[(q >> 1) * n + b] = s;
+            if (!use_mma) {
+                for (int e = tid; e < 2 * RES_RB * n; e += RES_THREADS) {
+                    const int q = e / n, b = e - q * n;
+                    double s = 0.0;
+                    for (int sl = 0; sl < S; sl++) s += sm.part[((size_t)sl * 2 * RES_RB + q) * n + b];
+                    if (q & 1) sm.vh[(q >> 1) * n + b] = s; else sm.zh[(q >> 1) * n + b] = s;
+                }
+                __syncthreads();
             }
-            __syncthreads();
             // C: one warp per run: violation of z, early-out test, multiplier bisection.  Meanwhile two of the idle warps per
             //    run do what the run's home CTA needs from z alone: the objective f0(z) (exact, from the stored form) and
             //    |z - last_z|^2 (qcqp.py:241)
@@ -488,7 +520,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                 if (lane == 0) res_run_view(ws, run0 + b0 + warp, n, m).viol[ci] = violation_of(relop, fz);
                 int early = 0;
                 if (relop == QCQP_RELOP_LE && fv <= 0) early = 1;   // onecons_qcqp returns z + u itself (utilities.py:157-158)
-                else res_bisect(sm.lam, sm.qh, vh, sm.xh + warp * n, rj, n, lane);
+                else if (use_mma) res_bisect(sm.lam, sm.qh, vh, sm.xh + warp, RES_RB, rj, n, lane);
+                else res_bisect(sm.lam, sm.qh, vh, sm.xh + warp * n, 1, rj, n, lane);
                 if (lane == 0) sm.flag[warp] = early ? -1 : sm.flag[warp];
             } else if (warp >= RES_RB && warp < RES_RB + 2 * nb) {
                 const int q = (warp - RES_RB) >> 1, job = (warp - RES_RB) & 1;
@@ -510,8 +543,25 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                 }
             }
             __syncthreads();
-            // D: x = Q xhat for the runs that were projected
-            {
+            // D: x = Q xhat for the runs that were projected (tensor-core tiles: a warp owns 8 outputs a, columns = runs, k walks b)
+            if (use_mma) {
+                const int gq = lane >> 2, tq = lane & 3;
+                for (int mt = warp; mt < (n >> 3); mt += RES_WARPS) {
+                    const int aa0 = mt << 3;
+                    double c0[4] = {0.0, 0.0, 0.0, 0.0}, c1[4] = {0.0, 0.0, 0.0, 0.0};
+                    int bb = 0;
+                    for (; bb + 16 <= n; bb += 16) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            dmma_m8n8k4(c0[u], c1[u], sm.Q[(aa0 + gq) * ldq + bb + 4 * u + tq], (gq < RES_RB) ? sm.xh[(bb + 4 * u + tq) * RES_RB + gq] : 0.0);
+                    }
+                    for (; bb < n; bb += 4) dmma_m8n8k4(c0[0], c1[0], sm.Q[(aa0 + gq) * ldq + bb + tq], (gq < RES_RB) ? sm.xh[(bb + tq) * RES_RB + gq] : 0.0);
+                    if (tq < RES_RB / 2) {
+                        sm.part[(2 * tq) * n + aa0 + gq] = (c0[0] + c0[1]) + (c0[2] + c0[3]);
+                        sm.part[(2 * tq + 1) * n + aa0 + gq] = (c1[0] + c1[1]) + (c1[2] + c1[3]);
+                    }
+                }
+            } else {
                 const int slice = tid / nb32, a = tid - slice * nb32;
                 double acc[RES_RB];
 #pragma unroll
@@ -536,7 +586,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) admm_res_kernel(const __grid_c
                 if (sm.flag[q] == -1) xv = sm.vs[e];
                 else {
                     xv = 0.0;
-                    for (int sl = 0; sl < S; sl++) xv += sm.part[((size_t)sl * RES_RB + q) * n + a];
+                    for (int sl = 0; sl < (use_mma ? 1 : S); sl++) xv += sm.part[((size_t)sl * RES_RB + q) * n + a];
                 }
                 double* up = sm.u + (size_t)(b0 + q) * n + a;
                 const double un = *up + (sm.zs[e] - xv);
@@ -674,10 +724,14 @@ bool admm_res_plan(const qcqp_pack* p, int runs, ResK* k, size_t* smem_bytes)
     const int nb32 = (v.n + 31) / 32 * 32;
     if (nb32 > RES_THREADS || v.n > 32 * RES_EPL) return false;
     const int S = RES_THREADS / nb32;
-    size_t doubles = (size_t)v.n * (v.n + 1) + 2 * (size_t)v.n + (size_t)rpg * v.n + 5 * (size_t)RES_RB * v.n +
+    const bool mma = (v.n & 7) == 0 && !getenv("QCQP_ADMM_NO_MMA");
+    const int ldq = mma ? v.n + ((4 - (v.n & 15) + 16) & 15) : v.n + 1;
+    size_t doubles = (size_t)v.n * ldq + 2 * (size_t)v.n + (size_t)rpg * v.n + 7 * (size_t)RES_RB * v.n +
                      (size_t)S * 2 * RES_RB * v.n + 2 * (size_t)v.n + RES_WARPS + 8 + 2 * (size_t)((rpg + v.m - 1) / v.m) + 2 + (size_t)v.n + (size_t)(rpg + 1) / 2 + 1;
     size_t bytes = doubles * 8 + 64;
     if (bytes > (size_t)max_smem_optin(p->device)) return false;
+    k->no_mma = getenv("QCQP_ADMM_NO_MMA") ? 1 : 0;
+    k->ldq = ldq;
     k->G = G; k->rpg = rpg; k->S = S; k->nb32 = nb32; k->runs = runs;
     *smem_bytes = bytes;
     return true;

@@ -768,6 +768,14 @@ int admm_res_try(qcqp_pack* p, const qcqp_admm_params* prm, const double* drhos,
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device);
     if (!coop || !admm_res_plan(p, K * R, &plan, &smem)) return QCQP_OK;
+    // the group barriers need every CTA resident: check the grid against the occupancy of this kernel on this device
+    int per_sm = 0;
+    if (cudaFuncSetAttribute(admm_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, admm_res_kernel, RES_THREADS, smem) != cudaSuccess ||
+        (long long)per_sm * num_sms(p->device) < (long long)p->v.m * plan.G) {
+        cudaGetLastError();
+        return QCQP_OK;
+    }
     *used = true;
     return admm_res_launch(p, prm, plan, smem, drhos, dZinv, K, dX0, R, dX, df0, dmv, dstats, stream);
 }

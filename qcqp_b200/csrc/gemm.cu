@@ -1,9 +1,11 @@
 // gemm.cu -- the dense FP64 contractions of the path as one shared-memory-tiled kernel:
 //   * SDR sampler      X = Z F + mu                      (np.random.multivariate_normal's  mean + z @ factor, qcqp.py:396)
 //   * dense quadratic forms of a batch   f_j(x_s) = x_s' P_j x_s   as  rowdot(X P_j, X)   (QuadraticFunction.eval, utilities.py:49-50)
-// 64x64 CTA tile, K-tile 16, 256 threads x (4x4) register tile, FP64 FMA pipe.  tcgen05 has no f64 kind and on B200 the DMMA
-// path has the same 40 TFLOP/s as the FMA pipe, so there is no tensor-core variant of this kernel.
+// Two kernels: dgemm_mma_kernel (default) runs on the FP64 tensor pipe (mma.sync.m8n8k4.f64; tcgen05 has no f64 kind);
+// dgemm_tile_kernel is the FMA-pipe version (64x64 CTA tile, K-tile 16, 4x4 register tile), kept for A/B runs (QCQP_GEMM_FMA=1).
 // Row dots are reduced in a fixed order (per-column-block partials, then a fixed-order sum) so results are reproducible.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace qcqp {
@@ -96,9 +98,131 @@ __global__ void __launch_bounds__(256) dgemm_tile_kernel(int M, int N, int K, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FP64 tensor-core variant (mma.sync.m8n8k4.f64, "DMMA"): the dense batched contraction of the path on the tensor pipe.
+// CTA tile 128 x 64, K-tile 16, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 DMMA tiles (32 accumulators per lane).
+// Fragments (PTX ISA): a = A[lane/4][lane%4], b = B[lane%4][lane/4], c0/c1 = C[lane/4][2 (lane%4) + {0,1}].
+// Shared tiles are padded so every fragment load is 2 wavefronts: A row stride 20 (= 4 mod 16), B row stride 72 (= 8 mod 16).
+// The next K-tile is fetched into registers while the current one is multiplied.  Per k-step of 4 a warp issues 8 LDS for 16
+// DMMAs (4096 FMAs) -- the FMA-pipe kernel above needs 8 LDS per 16 FMAs per lane and is shared-memory bound at 20 % of peak.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TB_M = 128, TB_N = 64, TB_K = 16, TA_LD = TB_K + 4, TBB_LD = TB_N + 8;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256) dgemm_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
+                                                        const double* __restrict__ B, int ldb, const double* __restrict__ bias,
+                                                        double* __restrict__ C, int ldc, const double* __restrict__ D, int ldd,
+                                                        double* __restrict__ part)
+{
+    __shared__ __align__(16) double As[TB_M * TA_LD];
+    __shared__ __align__(16) double Bs[TB_K * TBB_LD];
+    __shared__ double red[2][TB_M];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;            // warp tile origin: rows wm*32, cols wn*32
+    const int row0 = blockIdx.y * TB_M, col0 = blockIdx.x * TB_N;
+    double c0[4][4], c1[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { c0[i][j] = 0.0; c1[i][j] = 0.0; }
+
+    // loaders: A tile 128 x 16 (thread: row tid/2, 8 consecutive k), B tile 16 x 64 (thread: k tid/16, 4 consecutive columns)
+    const int a_r = tid >> 1, a_k = (tid & 1) * 8;
+    const int b_k = tid >> 4, b_c = (tid & 15) * 4;
+    double ra[8], rb[4];
+    auto fetch = [&](int k0) {
+        const int gr = row0 + a_r;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int gk = k0 + a_k + u;
+            ra[u] = (gr < M && gk < K) ? A[(size_t)gr * lda + gk] : 0.0;
+        }
+        const int gk = k0 + b_k;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int gc = col0 + b_c + u;
+            rb[u] = (gk < K && gc < N) ? B[(size_t)gk * ldb + gc] : 0.0;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += TB_K) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) As[a_r * TA_LD + a_k + u] = ra[u];
+#pragma unroll
+        for (int u = 0; u < 4; u++) Bs[b_k * TBB_LD + b_c + u] = rb[u];
+        __syncthreads();
+        if (k0 + TB_K < K) fetch(k0 + TB_K);
+#pragma unroll
+        for (int kk = 0; kk < TB_K; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) af[i] = As[(wm * 32 + i * 8 + g) * TA_LD + kk + tq];
+#pragma unroll
+            for (int j = 0; j < 4; j++) bf[j] = Bs[(kk + tq) * TBB_LD + wn * 32 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(c0[i][j], c1[i][j], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+    if (EPI == EPI_BIAS_STORE) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int gr = row0 + wm * 32 + i * 8 + g;
+            if (gr >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int gc = col0 + wn * 32 + j * 8 + 2 * tq;
+                if (gc < N) C[(size_t)gr * ldc + gc] = c0[i][j] + (bias ? bias[gc] : 0.0);
+                if (gc + 1 < N) C[(size_t)gr * ldc + gc + 1] = c1[i][j] + (bias ? bias[gc + 1] : 0.0);
+            }
+        }
+    } else {
+        // row dot with D over this CTA's 64 columns, reduced in a fixed order: lane's columns, the 4 lanes of a row, the 2 N-warps
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int lr = wm * 32 + i * 8 + g, gr = row0 + lr;
+            double s = 0.0;
+            if (gr < M) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int gc = col0 + wn * 32 + j * 8 + 2 * tq;
+                    if (gc < N) s = fma(c0[i][j], D[(size_t)gr * ldd + gc], s);
+                    if (gc + 1 < N) s = fma(c1[i][j], D[(size_t)gr * ldd + gc + 1], s);
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (tq == 0) red[wn][lr] = s;
+        }
+        __syncthreads();
+        if (tid < TB_M && row0 + tid < M) part[(size_t)blockIdx.x * M + row0 + tid] = red[0][tid] + red[1][tid];
+    }
+}
+
+static bool use_mma_gemm()
+{
+    static int v = -1;
+    if (v < 0) v = getenv("QCQP_GEMM_FMA") ? 0 : 1;     // QCQP_GEMM_FMA=1: the FMA-pipe kernel (A/B runs)
+    return v != 0;
+}
+
 // X = Z F + mu
 int gemm_sdr_launch(int S, int n, const double* dZ, const double* dF, const double* dmu, double* dX, cudaStream_t stream)
 {
+    if (use_mma_gemm()) {
+        dim3 gridm((n + TB_N - 1) / TB_N, (S + TB_M - 1) / TB_M);
+        dgemm_mma_kernel<EPI_BIAS_STORE><<<gridm, 256, 0, stream>>>(S, n, n, dZ, n, dF, n, dmu, dX, n, nullptr, 0, nullptr);
+        QCQP_CUDA_TRY(cudaGetLastError());
+        return QCQP_OK;
+    }
     dim3 grid((n + GB_N - 1) / GB_N, (S + GB_M - 1) / GB_M);
     dgemm_tile_kernel<EPI_BIAS_STORE><<<grid, 256, 0, stream>>>(S, n, n, dZ, n, dF, n, dmu, dX, n, nullptr, 0, nullptr);
     QCQP_CUDA_TRY(cudaGetLastError());
@@ -108,6 +232,12 @@ int gemm_sdr_launch(int S, int n, const double* dZ, const double* dF, const doub
 // part[cb][s] = sum over column block cb of (X P)[s][c] X[s][c];  returns the number of column blocks
 int gemm_quadform_launch(int S, int n, const double* dX, const double* dPj, int ld, double* dpart, cudaStream_t stream)
 {
+    if (use_mma_gemm()) {
+        dim3 gridm((n + TB_N - 1) / TB_N, (S + TB_M - 1) / TB_M);
+        dgemm_mma_kernel<EPI_ROWDOT><<<gridm, 256, 0, stream>>>(S, n, n, dX, n, dPj, ld, nullptr, nullptr, 0, dX, n, dpart);
+        QCQP_CUDA_TRY(cudaGetLastError());
+        return QCQP_OK;
+    }
     dim3 grid((n + GB_N - 1) / GB_N, (S + GB_M - 1) / GB_M);
     dgemm_tile_kernel<EPI_ROWDOT><<<grid, 256, 0, stream>>>(S, n, n, dX, n, dPj, ld, nullptr, nullptr, 0, dX, n, dpart);
     QCQP_CUDA_TRY(cudaGetLastError());
@@ -117,6 +247,12 @@ int gemm_quadform_launch(int S, int n, const double* dX, const double* dPj, int 
 // C = A B, no epilogue extras
 int gemm_plain_launch(int M, int N, int K, const double* dA, int lda, const double* dB, int ldb, double* dC, int ldc, cudaStream_t stream)
 {
+    if (use_mma_gemm()) {
+        dim3 gridm((N + TB_N - 1) / TB_N, (M + TB_M - 1) / TB_M);
+        dgemm_mma_kernel<EPI_BIAS_STORE><<<gridm, 256, 0, stream>>>(M, N, K, dA, lda, dB, ldb, nullptr, dC, ldc, nullptr, 0, nullptr);
+        QCQP_CUDA_TRY(cudaGetLastError());
+        return QCQP_OK;
+    }
     dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
     dgemm_tile_kernel<EPI_BIAS_STORE><<<grid, 256, 0, stream>>>(M, N, K, dA, lda, dB, ldb, nullptr, dC, ldc, nullptr, 0, nullptr);
     QCQP_CUDA_TRY(cudaGetLastError());

@@ -12,7 +12,7 @@
 //   with partner distance < the warp's region need only __syncwarp  ->  chunked prefix-max scan, one chunk per warp
 //   ->  thread 0: minimiser + MT19937 draws  ->  every thread updates the cached f_j of its incidences.
 // T is chosen from the number of restarts so that all of them are resident at once (128 registers per thread):
-// T = 512 for R <= 148, 256 for R <= 296, else 128 (4 CTAs per SM).
+// T = 512 for R <= 148, 256 for R <= 296, else 128 (4 CTAs per SM; beyond 592 restarts a 64-register build with 8 CTAs per SM).
 #include "cd_holes.cuh"
 #include "cd_shared.cuh"
 #include "common.cuh"
@@ -384,8 +384,8 @@ __device__ __noinline__ double blk_refresh_fvals(const PackView& P, const double
     return mx;
 }
 
-template <int T>
-__global__ void __launch_bounds__(T, 512 / T) cd_blk_kernel(const __grid_constant__ PackView P, CdK prm, BlkLayout lay,
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__ PackView P, CdK prm, BlkLayout lay,
                                                             const double* __restrict__ X0, int R, qcqp_rng_state* rngs, double* __restrict__ X,
                                                             double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out,
                                                             double* ws_fval, double* ws_scr, int* ws_scrj)
@@ -665,12 +665,12 @@ bool blk_wanted(const qcqp_pack* p)
     return p->info.incidences >= (int64_t)48 * v.n;   // on average a warp's worth of incident forms (or more) per coordinate
 }
 
-template <int T>
+template <int T, int MINB>
 static int blk_launch_t(qcqp_pack* p, const CdK& k, const BlkLayout& L, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0,
                         double* dmv, qcqp_cd_stats* dstats, double* ws_fval, double* ws_scr, int* ws_scrj, cudaStream_t stream)
 {
-    QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_blk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    cd_blk_kernel<T><<<R, T, L.total, stream>>>(p->v, k, L, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj);
+    QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_blk_kernel<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    cd_blk_kernel<T, MINB><<<R, T, L.total, stream>>>(p->v, k, L, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj);
     QCQP_CUDA_TRY(cudaGetLastError());
     return QCQP_OK;
 }
@@ -723,9 +723,13 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     double* ws_fval = (double*)p->ws;
     double* ws_scr = (double*)((char*)p->ws + a1);
     int* ws_scrj = (int*)((char*)p->ws + a1 + a2);
-    if (T == 512) return blk_launch_t<512>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
-    if (T == 256) return blk_launch_t<256>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
-    return blk_launch_t<128>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
+    // more restarts than 4 CTAs per SM can hold: the 64-register build of the 128-thread kernel, 8 CTAs per SM
+    const char* f8 = getenv("QCQP_BLK_CTAS");
+    const bool dense8 = (T == 128) && (f8 ? atoi(f8) == 8 : R > 4 * sms);
+    if (dense8) return blk_launch_t<128, 8>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
+    if (T == 512) return blk_launch_t<512, 1>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
+    if (T == 256) return blk_launch_t<256, 2>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
+    return blk_launch_t<128, 4>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
 }
 
 }  // namespace qcqp

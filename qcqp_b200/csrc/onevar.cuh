@@ -445,8 +445,20 @@ QCQP_HD int choose_point_det(double p, double q, double r, double lo0, double hi
     if (p == 0.0 && q == 0.0) return 2;
     const bool two = (nC == 2);
     if (p > 0.0) {
-        const double x0 = -q / (2. * p);
-        if ((lo0 <= x0 && x0 <= hi0) || (two && lo1 <= x0 && x0 <= hi1)) { *xout = x0; return 1; }
+        // x0 = -q / (2p) matters only if it lies in a piece.  With d = 2p > 0, x0 in [lo, hi] needs d lo <= -q <= d hi up to
+        // rounding: when -q misses both products by far more than any rounding error (2^-50 relative), the reference's test
+        // is false whatever the last bit of the quotient, and the 125-cycle division is skipped.  Otherwise: the exact test.
+        const double d = 2. * p, mq = -q;
+        const double a0 = d * lo0, b0 = d * hi0;
+        bool out = (mq < a0 - fabs(a0) * 8.9e-16) || (mq > b0 + fabs(b0) * 8.9e-16);
+        if (out && two) {
+            const double a1 = d * lo1, b1 = d * hi1;
+            out = (mq < a1 - fabs(a1) * 8.9e-16) || (mq > b1 + fabs(b1) * 8.9e-16);
+        }
+        if (!out) {
+            const double x0 = -q / (2. * p);
+            if ((lo0 <= x0 && x0 <= hi0) || (two && lo1 <= x0 && x0 <= hi1)) { *xout = x0; return 1; }
+        }
     }
     const double v0 = onevar_eval(p, q, r, lo0), v1 = onevar_eval(p, q, r, hi0);
     const double v2 = two ? onevar_eval(p, q, r, lo1) : QCQP_INF, v3 = two ? onevar_eval(p, q, r, hi1) : QCQP_INF;

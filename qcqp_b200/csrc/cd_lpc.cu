@@ -406,21 +406,33 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
             // ---- dense objective: blocked Gauss-Seidel.  All moves inside a 32-coordinate pass are resolved in registers with
             // the 32 x 32 diagonal block of P_0 (one coalesced fetch per pass); the rest of g is brought up to date once, after
             // the pass, with the rows of every coordinate that moved in flight together. ----
+            // the per-coordinate constants of a pass (constraint triple, relop, P_0[k,k], q_0[k]) are loaded one pass ahead: they
+            // come from L2 (the rows of P_0 stream through L1) and would otherwise open every pass with a full round trip
+            double n_p = 0.0, n_q = 0.0, n_r = 0.0, n_od = 0.0, n_oq = 0.0;
+            int n_rel = 0;
+            if (V.obj_dense && lane < n) { n_p = V.c_p[lane]; n_q = V.c_q[lane]; n_r = V.c_r[lane]; n_rel = V.c_rel[lane]; n_od = V.o_diag[lane]; n_oq = V.o_q[lane]; }
             for (int k0 = 0; V.obj_dense && k0 < n && !done; k0 += 32) {
                 const int B = (n - k0 < 32) ? (n - k0) : 32;
                 const bool act = lane < B;
                 const int k = k0 + lane;
                 double xk = 0.0, p0 = 0.0, oq = 0.0, gl = 0.0, q0 = 0.0, r0 = f0val, xi = 0.0, mydelta = 0.0;
                 int rc = 0;
+                const double c_pk = n_p, c_qk = n_q, c_rk = n_r, c_odk = n_od, c_oqk = n_oq;
+                const int c_relk = n_rel;
+                {
+                    int kn = k + 32;
+                    if (kn >= n) kn = lane;                      // the next sweep starts over at coordinate `lane`
+                    if (kn < n) { n_p = V.c_p[kn]; n_q = V.c_q[kn]; n_r = V.c_r[kn]; n_rel = V.c_rel[kn]; n_od = V.o_diag[kn]; n_oq = V.o_q[kn]; }
+                }
                 if (act) {
-                    const double p = V.c_p[k], q = V.c_q[k], r = V.c_r[k];
-                    const int rel = V.c_rel[k];
+                    const double p = c_pk, q = c_qk, r = c_rk;
+                    const int rel = c_relk;
                     xk = w.x[k];
                     if (!(mrel == rel && mp == p && mq == q && mr == r)) {
                         mnC = single_constraint_pieces(p, q, r, rel, viol_p2, &ml0, &mh0, &ml1, &mh1);
                         mp = p; mq = q; mr = r; mrel = rel;
                     }
-                    p0 = V.o_diag[k]; oq = V.o_q[k]; gl = w.g[k];
+                    p0 = c_odk; oq = c_oqk; gl = w.g[k];
                     q0 = 2 * (gl - p0 * xk) + oq;
                     r0 = f0val - xk * (p0 * xk + q0);
                     rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);

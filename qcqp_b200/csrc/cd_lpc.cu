@@ -205,7 +205,7 @@ __device__ __forceinline__ void lpc_axpy_multi(const PackView& P, const LpcMem& 
 // stage 1: phase 1 only (x, stream and stats are written back).   stage 2: phase 2 only, starting from stage 1's output with
 // g = P_0 x supplied in G (one tiled GEMM for all restarts instead of one latency-bound GEMV per warp); the returned
 // (f0, maxviol) then come from the batched eval kernels.
-__global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK prm, int stage, const double* __restrict__ X0, int R,
+__global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, CdK prm, int stage, const double* __restrict__ X0, int R,
                                                      qcqp_rng_state* rngs, double* X, const double* __restrict__ G,
                                                      double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out)
 {
@@ -424,6 +424,15 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
                     if (kn >= n) kn = lane;                      // the next sweep starts over at coordinate `lane`
                     if (kn < n) { n_p = V.c_p[kn]; n_q = V.c_q[kn]; n_r = V.c_r[kn]; n_rel = V.c_rel[kn]; n_od = V.o_diag[kn]; n_oq = V.o_q[kn]; }
                 }
+                // diagonal block D[i][j] = P_0[k0+i][k0+j]: iteration i loads row i coalesced (lane = column).  The loads are issued
+                // before the lanes evaluate their coordinates (85 % of the passes have a candidate mover and need the block), so
+                // the round trip overlaps that evaluation; the block is parked in shared memory only if a candidate exists.
+                double dv[32];
+                {
+                    const double* base = P.dense_P + (size_t)k0 * P.ld + k0;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) dv[i] = (i < B && act) ? __ldg(base + (size_t)i * P.ld + lane) : 0.0;
+                }
                 if (act) {
                     const double p = c_pk, q = c_qk, r = c_rk;
                     const int rel = c_relk;
@@ -437,13 +446,7 @@ __global__ void __launch_bounds__(32) cd_lpc_kernel(PackView P, LpcView V, CdK p
                     r0 = f0val - xk * (p0 * xk + q0);
                     rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
                 }
-                // diagonal block D[i][j] = P_0[k0+i][k0+j], fetched only when the pass has a candidate mover:
-                // iteration i loads row i coalesced (lane = column)
                 if (__ballot_sync(FULL, act && (rc == 2 || (rc == 1 && fabs(xi - xk) > tol)))) {
-                    const double* base = P.dense_P + (size_t)k0 * P.ld + k0;
-                    double dv[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i++) dv[i] = (i < B && act) ? __ldg(base + (size_t)i * P.ld + lane) : 0.0;
 #pragma unroll
                     for (int i = 0; i < 32; i++) w.blk[i * 32 + lane] = dv[i];
                 }

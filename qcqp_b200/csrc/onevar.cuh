@@ -118,10 +118,13 @@ constexpr double IVAL_TOL = 1e-4;  // the default tol of get_feasible_intervals;
 // {x : p x^2 + q x + rr <= 0}; the '<=' branch of utilities.py:210-231 with s already folded into rr
 QCQP_HD int ivals_le0(double p, double q, double rr, Ival* out)
 {
+    // q == 0 (x_k^2 = c constraints: Boolean LS, MAXCUT): -q - rD and -q + rD are exactly -rD and +rD, and IEEE division is
+    // sign-symmetric, so the two roots are one quotient and its negation -- same bits, one division less
     if (p > IVAL_TOL) {
         double D = q * q - (4 * p) * rr;
         if (D >= 0) {
             double rD = sqrt(D), den = 2 * p;
+            if (q == 0.0) { const double h = rD / den; out[0].lo = -h; out[0].hi = h; return 1; }
             out[0].lo = (-q - rD) / den;
             out[0].hi = (-q + rD) / den;
             return 1;
@@ -132,6 +135,12 @@ QCQP_HD int ivals_le0(double p, double q, double rr, Ival* out)
         double D = q * q - (4 * p) * rr;
         if (D >= 0) {
             double rD = sqrt(D), den = 2 * p;
+            if (q == 0.0) {
+                const double h = rD / den;
+                out[0].lo = -QCQP_INF; out[0].hi = h;
+                out[1].lo = -h; out[1].hi = QCQP_INF;
+                return 2;
+            }
             out[0].lo = -QCQP_INF; out[0].hi = (-q + rD) / den;
             out[1].lo = (-q - rD) / den; out[1].hi = QCQP_INF;
             return 2;
@@ -422,13 +431,49 @@ QCQP_HD int choose_point(double p, double q, double r, const double* c_lo, const
 QCQP_HD int single_constraint_pieces(double p, double q, double r, int rel, double s, double* lo0, double* hi0, double* lo1,
                                      double* hi1)
 {
-    Fold f;
-    f.init();
-    f.mcnt = 1;
     Ival I[2];
     I[0].lo = I[0].hi = I[1].lo = I[1].hi = 0.0;
     const int c = feasible_intervals(p, q, r, rel, s, I);
+    *lo0 = *hi0 = *lo1 = *hi1 = 0.0;
     if (c == 0) return 0;
+    // The intervals of one constraint come out in ascending order (lo0 <= hi0 <= lo1 <= hi1), so the event list
+    // -inf, lo0, hi0[, lo1, hi1], +inf of the reference's sweep (utilities.py:245-261) is already sorted: scan it directly --
+    // equal keys share one counter, zero-net keys are dropped, a piece ends where the total falls to m = 1 by exactly -1.
+    const bool sorted = (c == 1) ? (I[0].lo <= I[0].hi) : (I[0].lo <= I[0].hi && I[0].hi <= I[1].lo && I[1].lo <= I[1].hi);
+    if (sorted) {
+        double k[6];
+        int d[6];
+        int ne;
+        k[0] = -QCQP_INF; d[0] = +1;
+        k[1] = I[0].lo; d[1] = +1;
+        k[2] = I[0].hi; d[2] = -1;
+        if (c == 2) { k[3] = I[1].lo; d[3] = +1; k[4] = I[1].hi; d[4] = -1; k[5] = QCQP_INF; d[5] = -1; ne = 6; }
+        else { k[3] = QCQP_INF; d[3] = -1; k[4] = k[5] = QCQP_INF; d[4] = d[5] = 0; ne = 4; }
+        double cl[2], ch[2];
+        cl[0] = cl[1] = ch[0] = ch[1] = 0.0;
+        int nC = 0, tot = 0;
+        double prev_key = 0.0, cur_key = k[0];
+        int cur_d = d[0];
+        bool have_prev = false;
+#pragma unroll
+        for (int i = 1; i <= 6; i++) {
+            if (i < ne && k[i] == cur_key) { cur_d += d[i]; continue; }
+            if (i <= ne) {
+                if (cur_d != 0) {
+                    tot += cur_d;
+                    if (tot == 1 && cur_d == -1 && have_prev) { if (nC < 2) { cl[nC] = prev_key; ch[nC] = cur_key; } nC++; }
+                    prev_key = cur_key;
+                    have_prev = true;
+                }
+                if (i < ne) { cur_key = k[i]; cur_d = d[i]; }
+            }
+        }
+        *lo0 = cl[0]; *hi0 = ch[0]; *lo1 = cl[1]; *hi1 = ch[1];
+        return nC;
+    }
+    Fold f;
+    f.init();
+    f.mcnt = 1;
     if (c == 1) f.add_single(I[0].lo, I[0].hi);
     double cl[4], ch[4];
     cl[0] = cl[1] = ch[0] = ch[1] = 0.0;

@@ -40,7 +40,10 @@ pack = engine.Pack(forms)
 for R, iters in ((64, 10), (512, 10), (512, 40)):
     X0 = np.random.RandomState(5).randn(R, 401)
     rng = engine.rng_states(seeds=np.arange(R))
-    t0 = time.perf_counter(); X, f0, mv, st = pack.cd_improve(X0, rng, num_iters=iters); dt = time.perf_counter() - t0
+    dt = 1e9
+    for _rep in range(2):       # the first call at a new size grows the pack's workspace (cudaMalloc): time the second
+        rng = engine.rng_states(seeds=np.arange(R))
+        t0 = time.perf_counter(); X, f0, mv, st = pack.cd_improve(X0, rng, num_iters=iters); dt = min(dt, time.perf_counter() - t0)
     sw1 = sum(s.steps_p1 for s in st) / 401.0; sw2 = sum(s.steps_p2 for s in st) / 401.0
     out["C5_circle_200_R%d_%dsweeps" % (R, iters)] = dict(seconds=dt, restart_sweeps=sw1 + sw2, restart_sweeps_p1=sw1, restart_sweeps_p2=sw2,
                                                           restart_sweeps_per_s=(sw1 + sw2) / dt, max_violation=float(mv.max()),

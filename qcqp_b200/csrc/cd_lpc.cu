@@ -429,9 +429,15 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                 // the round trip overlaps that evaluation; the block is parked in shared memory only if a candidate exists.
                 double dv[32];
                 {
-                    const double* base = P.dense_P + (size_t)k0 * P.ld + k0;
+                    const double* pp = P.dense_P + (size_t)k0 * P.ld + k0 + lane;
+                    if (B == 32) {
+                        // full block (all passes but the last of a sweep): no per-element predicates, one pointer bump per row
 #pragma unroll
-                    for (int i = 0; i < 32; i++) dv[i] = (i < B && act) ? __ldg(base + (size_t)i * P.ld + lane) : 0.0;
+                        for (int i = 0; i < 32; i++) { dv[i] = __ldg(pp); pp += P.ld; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) dv[i] = (i < B && act) ? __ldg(pp + (size_t)i * P.ld) : 0.0;
+                    }
                 }
                 if (act) {
                     const double p = c_pk, q = c_qk, r = c_rk;

@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
         // per-lane memo of the constraint's pieces at the frozen level
         double mp = 0.0, mq = 0.0, mr = 0.0, ml0 = 0.0, mh0 = 0.0, ml1 = 0.0, mh1 = 0.0;
         int mrel = -1, mnC = 0;
+        bool mfin = false;      // every endpoint of the memoised pieces is finite
         for (int t = 0; t < prm.num_iters && !done; t++) {
             st.sweeps_p2++;
             // ---- dense objective: blocked Gauss-Seidel.  All moves inside a 32-coordinate pass are resolved in registers with
@@ -445,12 +446,13 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                     xk = w.x[k];
                     if (!(mrel == rel && mp == p && mq == q && mr == r)) {
                         mnC = single_constraint_pieces(p, q, r, rel, viol_p2, &ml0, &mh0, &ml1, &mh1);
+                        mfin = mnC > 0 && mnC <= 2 && !is_inf(ml0) && !is_inf(mh0) && (mnC < 2 || (!is_inf(ml1) && !is_inf(mh1)));
                         mp = p; mq = q; mr = r; mrel = rel;
                     }
                     p0 = c_odk; oq = c_oqk; gl = w.g[k];
                     q0 = 2 * (gl - p0 * xk) + oq;
                     r0 = f0val - xk * (p0 * xk + q0);
-                    rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
+                    rc = mfin ? choose_point_det_t<true>(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi) : choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
                 }
                 if (__ballot_sync(FULL, act && (rc == 2 || (rc == 1 && fabs(xi - xk) > tol)))) {
 #pragma unroll
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                             gl = fma(w.blk[first * 32 + lane], delta, gl);     // D[lane][first] = D[first][lane]
                             q0 = 2 * (gl - p0 * xk) + oq;
                             r0 = f0val - xk * (p0 * xk + q0);
-                            rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
+                            rc = mfin ? choose_point_det_t<true>(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi) : choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
                         }
                     } else {
                         uc++;

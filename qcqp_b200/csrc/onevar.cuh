@@ -484,7 +484,9 @@ QCQP_HD int single_constraint_pieces(double p, double q, double r, int rel, doub
 
 // The part of choose_point that needs no random number, for at most two pieces:
 //   0 = None, 1 = *xout found deterministically, 2 = the reference would draw (flat objective or tied endpoints).
-QCQP_HD int choose_point_det(double p, double q, double r, double lo0, double hi0, double lo1, double hi1, int nC, double* xout)
+// FIN: the caller knows every endpoint is finite (memoised with the pieces), so OneVarQuadraticFunction.eval's +-inf branches drop out
+template <bool FIN>
+QCQP_HD int choose_point_det_t(double p, double q, double r, double lo0, double hi0, double lo1, double hi1, int nC, double* xout)
 {
     if (nC == 0) return 0;
     if (p == 0.0 && q == 0.0) return 2;
@@ -505,19 +507,22 @@ QCQP_HD int choose_point_det(double p, double q, double r, double lo0, double hi
             if ((lo0 <= x0 && x0 <= hi0) || (two && lo1 <= x0 && x0 <= hi1)) { *xout = x0; return 1; }
         }
     }
-    const double v0 = onevar_eval(p, q, r, lo0), v1 = onevar_eval(p, q, r, hi0);
-    const double v2 = two ? onevar_eval(p, q, r, lo1) : QCQP_INF, v3 = two ? onevar_eval(p, q, r, hi1) : QCQP_INF;
-    double bestf = QCQP_INF;
-    if (v0 < bestf) bestf = v0;
-    if (v1 < bestf) bestf = v1;
-    if (v2 < bestf) bestf = v2;
-    if (v3 < bestf) bestf = v3;
+    const double v0 = FIN ? lo0 * (p * lo0 + q) + r : onevar_eval(p, q, r, lo0);
+    const double v1 = FIN ? hi0 * (p * hi0 + q) + r : onevar_eval(p, q, r, hi0);
+    const double v2 = two ? (FIN ? lo1 * (p * lo1 + q) + r : onevar_eval(p, q, r, lo1)) : QCQP_INF;
+    const double v3 = two ? (FIN ? hi1 * (p * hi1 + q) + r : onevar_eval(p, q, r, hi1)) : QCQP_INF;
+    // smallest non-NaN value, +inf if there is none: what the reference's running `if v < bestf` leaves behind (fmin ignores NaN)
+    const double bestf = fmin(fmin(fmin(v0, v1), fmin(v2, v3)), QCQP_INF);
     const bool m0 = (v0 == bestf), m1 = (v1 == bestf), m2 = two && (v2 == bestf), m3 = two && (v3 == bestf);
     const int cnt = (int)m0 + (int)m1 + (int)m2 + (int)m3;
     if (cnt == 0) return 0;
     if (cnt > 1) return 2;
     *xout = m0 ? lo0 : (m1 ? hi0 : (m2 ? lo1 : hi1));
     return 1;
+}
+QCQP_HD int choose_point_det(double p, double q, double r, double lo0, double hi0, double lo1, double hi1, int nC, double* xout)
+{
+    return choose_point_det_t<false>(p, q, r, lo0, hi0, lo1, hi1, nC, xout);
 }
 
 }  // namespace qcqp

@@ -471,12 +471,12 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                     uc += quiet;
                     st.steps_p2 += quiet;
                     if (first == B) break;
-                    const double fx = bcast(xk, first), fp0 = bcast(p0, first), fq0 = bcast(q0, first), fr0 = bcast(r0, first);
-                    double fxi = bcast(xi, first);
                     const int frc = bcast_i(rc, first);
                     st.steps_p2++;
                     bool found = true;
+                    double fx = 0.0, fxi = 0.0, fp0 = 0.0, fq0 = 0.0, fr0 = 0.0;
                     if (frc == 2) {
+                        fx = bcast(xk, first); fp0 = bcast(p0, first); fq0 = bcast(q0, first); fr0 = bcast(r0, first);
                         double cl[2], ch[2];
                         cl[0] = bcast(ml0, first); ch[0] = bcast(mh0, first); cl[1] = bcast(ml1, first); ch[1] = bcast(mh1, first);
                         const int nC = bcast_i(mnC, first);
@@ -492,11 +492,23 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                         if (err) { st.status = err; dead = true; done = true; break; }
                         found = fnd != 0;
                     }
-                    if (found && fabs(fxi - fx) > tol) {
-                        const double delta = fxi - fx;
+                    // frc == 1: the lane was picked because |xi - xk| > tol; it forms delta and f_0(x) = t0 + b (t2 b + t1) from its own
+                    // registers and only those two values travel.  frc == 2 (random draw, rare): everything was broadcast above.
+                    bool moves = true;
+                    double delta, f0new;
+                    if (frc == 2) {
+                        moves = found && fabs(fxi - fx) > tol;
+                        delta = fxi - fx;
+                        f0new = fr0 + fxi * (fp0 * fxi + fq0);
+                    } else {
+                        delta = bcast(xi - xk, first);
+                        f0new = bcast(r0 + xi * (p0 * xi + q0), first);
+                        fxi = xi;                                   // meaningful in lane `first` only
+                    }
+                    if (moves) {
                         if (lane == first) { w.x[k] = fxi; mydelta = delta; }
                         moved |= 1u << first;
-                        f0val = fr0 + fxi * (fp0 * fxi + fq0);        // f_0(x) = t0 + b (t2 b + t1)
+                        f0val = f0new;
                         uc = 0;
                         st.updates_p2++;
                         // the coordinates still to come see the move through their own entry of column `first`

@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
         } else {
             f0val = lpc_refresh(P, V, w, lane);
         }
-        long long uc = 0;
+        int uc = 0;                 // update_counter of phase 2 (qcqp.py:160): never exceeds n
         bool done = false;
         // per-lane memo of the constraint's pieces at the frozen level
         double mp = 0.0, mq = 0.0, mr = 0.0, ml0 = 0.0, mh0 = 0.0, ml1 = 0.0, mh1 = 0.0;
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                     const unsigned stop = __ballot_sync(FULL, wants_move || (pending && rc == 2));
                     const int first = stop ? (__ffs(stop) - 1) : B;
                     const int quiet = first - cur;      // steps that change nothing (qcqp.py:172-176)
-                    if ((long long)n - uc <= quiet) { st.steps_p2 += (n - uc); done = true; break; }
+                    if (n - uc <= quiet) { st.steps_p2 += (n - uc); done = true; break; }
                     uc += quiet;
                     st.steps_p2 += quiet;
                     if (first == B) break;
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                 const unsigned stop = __ballot_sync(FULL, wants_move || (act && rc == 2));
                 const int first = stop ? (__ffs(stop) - 1) : B;
                 // the `first` steps before it change nothing: update_counter += 1 each (qcqp.py:172-176)
-                if ((long long)n - uc <= first) { st.steps_p2 += (n - uc); done = true; break; }   // converged inside the run
+                if (n - uc <= first) { st.steps_p2 += (n - uc); done = true; break; }   // converged inside the run
                 uc += first;
                 st.steps_p2 += first;
                 if (first == B) { k0 += B; continue; }

@@ -69,6 +69,25 @@ __device__ __forceinline__ double lpc_refresh(const PackView& P, const LpcView& 
             const bool v0 = c < n2, v1 = c + 32 < n2, v2 = c + 64 < n2, v3 = c + 96 < n2;
             const double2 zz = make_double2(0.0, 0.0);
             int r = 0;
+            // 8 rows x 4 column groups = 32 sixteen-byte loads in flight per lane: the refresh is a latency-bound GEMV over the
+            // whole of P_0 by one warp, and the restarts that need it (>= 16 sweeps) are the ones that end the launch
+            for (; r + 8 <= n; r += 8) {
+                double2 t[8][4];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const double2* row = reinterpret_cast<const double2*>(M + (size_t)(r + u) * ld);
+                    t[u][0] = v0 ? __ldg(&row[c]) : zz; t[u][1] = v1 ? __ldg(&row[c + 32]) : zz;
+                    t[u][2] = v2 ? __ldg(&row[c + 64]) : zz; t[u][3] = v3 ? __ldg(&row[c + 96]) : zz;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const double xr = w.x[r + u];
+                    a0.x = fma(t[u][0].x, xr, a0.x); a0.y = fma(t[u][0].y, xr, a0.y);
+                    a1.x = fma(t[u][1].x, xr, a1.x); a1.y = fma(t[u][1].y, xr, a1.y);
+                    a2.x = fma(t[u][2].x, xr, a2.x); a2.y = fma(t[u][2].y, xr, a2.y);
+                    a3.x = fma(t[u][3].x, xr, a3.x); a3.y = fma(t[u][3].y, xr, a3.y);
+                }
+            }
             for (; r + 4 <= n; r += 4) {
                 double2 t[4][4];
 #pragma unroll

@@ -978,7 +978,7 @@ int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R,
         // separable problem (one single-coordinate constraint per coordinate): the lane-per-coordinate kernel
         CdK k0;
         k0.num_iters = prm->num_iters; k0.viol_tol = prm->viol_tol; k0.tol = prm->tol; k0.phase1 = prm->phase1; k0.mode = MODE_GRAD;
-        k0.refresh_every = prm->refresh_every > 0 ? prm->refresh_every : 16;
+        k0.refresh_every = prm->refresh_every > 0 ? prm->refresh_every : 64;
         return lpc_launch(p, k0, dX0, R, drng, dX, df0, dmv, dstats, stream);
     }
     int rc = plan_layout(p, R, mode == MODE_GRAD, &L);

@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                     xk = w.x[k];
                     if (!(mrel == rel && mp == p && mq == q && mr == r)) {
                         mnC = single_constraint_pieces(p, q, r, rel, viol_p2, &ml0, &mh0, &ml1, &mh1);
+                        mfin = mnC > 0 && mnC <= 2 && !is_inf(ml0) && !is_inf(mh0) && (mnC < 2 || (!is_inf(ml1) && !is_inf(mh1)));
                         mp = p; mq = q; mr = r; mrel = rel;
                     }
                     if (V.o_inc[k]) {
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                         q0 = 2 * (w.g[k] - p0 * xk) + V.o_q[k];
                         r0 = f0val - xk * (p0 * xk + q0);
                     }
-                    rc = choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
+                    rc = mfin ? choose_point_det_t<true>(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi) : choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
                 }
                 const bool wants_move = act && rc == 1 && fabs(xi - xk) > tol;
                 const unsigned stop = __ballot_sync(FULL, wants_move || (act && rc == 2));

@@ -136,7 +136,19 @@ __global__ void __launch_bounds__(256) dgemm_mma_kernel(int M, int N, int K, con
     const int a_r = tid >> 1, a_k = (tid & 1) * 8;
     const int b_k = tid >> 4, b_c = (tid & 15) * 4;
     double ra[8], rb[4];
+    // interior tiles with 16-byte aligned rows take 16-byte loads without bounds tests
+    const bool vec_ok = ((lda | ldb) & 1) == 0 && ((reinterpret_cast<size_t>(A) | reinterpret_cast<size_t>(B)) & 15) == 0 &&
+                        row0 + TB_M <= M && col0 + TB_N <= N;
     auto fetch = [&](int k0) {
+        if (vec_ok && k0 + TB_K <= K) {
+            const double2* ap = reinterpret_cast<const double2*>(A + (size_t)(row0 + a_r) * lda + k0 + a_k);
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const double2 t = __ldg(ap + u); ra[2 * u] = t.x; ra[2 * u + 1] = t.y; }
+            const double2* bp = reinterpret_cast<const double2*>(B + (size_t)(k0 + b_k) * ldb + col0 + b_c);
+#pragma unroll
+            for (int u = 0; u < 2; u++) { const double2 t = __ldg(bp + u); rb[2 * u] = t.x; rb[2 * u + 1] = t.y; }
+            return;
+        }
         const int gr = row0 + a_r;
 #pragma unroll
         for (int u = 0; u < 8; u++) {

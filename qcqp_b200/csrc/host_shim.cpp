@@ -93,5 +93,13 @@ extern "C" int qcqp_shim_single_det(const double* f0, const double* f, int32_t r
     int c = single_constraint_pieces(f[0], f[1], f[2], relop, s, &lo0, &hi0, &lo1, &hi1);
     pieces4[0] = lo0; pieces4[1] = hi0; pieces4[2] = lo1; pieces4[3] = hi1;
     *nC = c;
-    return choose_point_det(f0[0], f0[1], f0[2], lo0, hi0, lo1, hi1, c, xout);
+    const int rc = choose_point_det(f0[0], f0[1], f0[2], lo0, hi0, lo1, hi1, c, xout);
+    // the finite-endpoint variant the kernel uses on its hot path must agree with the general one whenever it applies
+    const bool fin = c > 0 && c <= 2 && !is_inf(lo0) && !is_inf(hi0) && (c < 2 || (!is_inf(lo1) && !is_inf(hi1)));
+    if (fin) {
+        double x2 = 0.0;
+        const int rc2 = choose_point_det_t<true>(f0[0], f0[1], f0[2], lo0, hi0, lo1, hi1, c, &x2);
+        if (rc2 != rc || (rc == 1 && !(x2 == *xout))) return -100;
+    }
+    return rc;
 }

@@ -148,6 +148,7 @@ def test_device_single_constraint_deterministic_choice(shim):
             err = True
         f0a = np.array(f0); fa = np.array([p, q, r]); out = C.c_double(); pieces = np.zeros(4); nC = C.c_int32()
         rc = shim.qcqp_shim_single_det(f0a.ctypes.data, fa.ctypes.data, orc.RELOP_CODE[rel], s, C.byref(out), pieces.ctypes.data, C.byref(nC))
+        assert rc != -100, "finite-endpoint chooser disagrees with the general one"
         drew = err or st.pos != pos0
         if rc == 2:
             assert drew or (f0[0] == 0 and f0[1] == 0), (t, f0, (p, q, r, rel), s)

@@ -46,8 +46,10 @@ int gemm_col_blocks(int n);
 
 // Batched path for packs with dense forms: x_s' P_j x_s of every dense form as a tiled FP64 GEMM with a row-dot epilogue
 // (gemm.cu), then this kernel -- one warp per point -- adds q_j.x + r_j, evaluates the sparse forms and reduces.
-__global__ void eval_finish_kernel(PackView P, const double* __restrict__ X, int R, const double* __restrict__ part, int ncb,
-                                   double* __restrict__ f0, double* __restrict__ maxviol, double* __restrict__ viol)
+// sep: separable pack (LpcView) and no per-constraint output: constraint k is (c_p x_k + c_q) x_k + c_r read from the
+// coordinate-major arrays -- the same operations in the same order as the generic one-entry form, without its index chasing.
+__global__ void eval_finish_kernel(PackView P, LpcView V, int sep, const double* __restrict__ X, int R, const double* __restrict__ part,
+                                   int ncb, double* __restrict__ f0, double* __restrict__ maxviol, double* __restrict__ viol)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,7 +71,16 @@ __global__ void eval_finish_kernel(PackView P, const double* __restrict__ X, int
                 mv = (vv > mv) ? vv : mv;
             }
         };
-        eval_forms(P, x, 0, m, false, lane, sink, /*skip_dense=*/true);
+        if (sep) {
+            eval_forms(P, x, 0, 0, false, lane, sink, /*skip_dense=*/true);      // a sparse objective, if any
+            for (int k = lane; k < n; k += 32) {
+                const double xk = x[k];
+                const double vv = violation_of(V.c_rel[k], (V.c_p[k] * xk + V.c_q[k]) * xk + V.c_r[k]);
+                mv = (vv > mv) ? vv : mv;
+            }
+        } else {
+            eval_forms(P, x, 0, m, false, lane, sink, /*skip_dense=*/true);
+        }
         for (int d = 0; d < P.n_dense; d++) {
             const int j = P.dense_form[d];
             double acc = 0.0;
@@ -105,7 +116,8 @@ int eval_launch(qcqp_pack* p, const double* dX, int R, double* df0, double* dmv,
         size_t smem = (size_t)wpb * ((n + 1) & ~1) * 8;
         if (smem > (size_t)max_smem_optin(p->device)) return fail(QCQP_ERR_CAPACITY, "qcqp_eval: n too large for the shared-memory staging of x");
         QCQP_CUDA_TRY(cudaFuncSetAttribute(eval_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eval_finish_kernel<<<(R + wpb - 1) / wpb, wpb * 32, smem, stream>>>(p->v, dX, R, part, ncb, df0, dmv, dviol);
+        eval_finish_kernel<<<(R + wpb - 1) / wpb, wpb * 32, smem, stream>>>(p->v, p->lpc, (p->lpc_ok && !dviol) ? 1 : 0, dX, R, part, ncb, df0, dmv,
+                                                                            dviol);
         QCQP_CUDA_TRY(cudaGetLastError());
         return QCQP_OK;
     }

@@ -163,18 +163,29 @@ QCQP_HD int feasible_intervals(double p, double q, double r, int relop, double s
         return ivals_le0(p, q, r - s, out);
     }
     Ival a[2], b[2];
-    int na = ivals_le0(p, q, r - s, a);       // f1 = (p, q, r - s) <= 0
-    int nb = ivals_le0(-p, -q, -r - s, b);    // f2 = (-p, -q, -r - s) <= 0
-    int c = 0;
-    for (int i = 0; i < na; i++)
-        for (int k = 0; k < nb; k++) {
-            double lo = (b[k].lo > a[i].lo) ? b[k].lo : a[i].lo;
-            double hi = (b[k].hi < a[i].hi) ? b[k].hi : a[i].hi;
-            if (lo <= hi) {
-                if (c < 2) { out[c].lo = lo; out[c].hi = hi; }
-                c++;
-            }
-        }
+    a[0].lo = a[0].hi = a[1].lo = a[1].hi = b[0].lo = b[0].hi = b[1].lo = b[1].hi = 0.0;
+    const int na = ivals_le0(p, q, r - s, a);       // f1 = (p, q, r - s) <= 0
+    const int nb = ivals_le0(-p, -q, -r - s, b);    // f2 = (-p, -q, -r - s) <= 0
+    // the reference's double loop over (i, k) in the order (0,0), (0,1), (1,0), (1,1), keeping the first two non-empty
+    // intersections -- written with static indices only, so that nothing here lives in local memory on the device
+    Ival t[4];
+    bool v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int i = e >> 1, k = e & 1;
+        t[e].lo = (b[k].lo > a[i].lo) ? b[k].lo : a[i].lo;
+        t[e].hi = (b[k].hi < a[i].hi) ? b[k].hi : a[i].hi;
+        v[e] = (i < na) && (k < nb) && (t[e].lo <= t[e].hi);
+    }
+    const int c = (int)v[0] + (int)v[1] + (int)v[2] + (int)v[3];
+    // first valid entry, then the first valid one after it
+    const Ival f1 = v[0] ? t[0] : (v[1] ? t[1] : (v[2] ? t[2] : t[3]));
+    const Ival s3 = t[3];
+    const Ival s2 = v[2] ? t[2] : s3;                 // first valid among {2, 3}
+    const Ival s1 = v[1] ? t[1] : s2;                 // first valid among {1, 2, 3}
+    const Ival f2 = v[0] ? s1 : (v[1] ? s2 : s3);      // first valid after the first valid
+    if (c >= 1) out[0] = f1;
+    if (c >= 2) out[1] = f2;
     return c > 2 ? 2 : c;
 }
 

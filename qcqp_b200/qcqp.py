@@ -1,7 +1,8 @@
 """The CVXPY-facing Suggest-and-Improve facade: same class, methods and return values as the reference's QCQP
 (qcqp/qcqp.py:367-432), with the hot path running on the B200 engine.
 
-    qcqp = QCQP(prob)                 # a QCQPForm / list of (P, q, r, relop) / (if cvxpy is importable) a cvxpy Problem
+    qcqp = QCQP(prob)                 # a qcqp_b200.model Problem (the cvxpy surface of the reference's examples) / a QCQPForm /
+                                      # a list of (P, q, r, relop) / (if cvxpy 0.4 is importable) a cvxpy Problem
     f, v = qcqp.suggest(SDR)          # (objective, max violation) of the suggested point
     f, v = qcqp.improve(COORD_DESCENT)
 
@@ -17,6 +18,7 @@ import scipy.sparse as sp
 from . import settings as s
 from . import engine
 from . import relax
+from . import model
 from .forms import QCQPForm, QuadraticFunction
 
 log = logging.getLogger("qcqp_b200")   # the reference opens ./qcqp.log at import time (qcqp.py:39); this package does not
@@ -59,6 +61,11 @@ class QCQP:
             self.qcqp_form = prob
         elif isinstance(prob, (list, tuple)):
             self.qcqp_form = QCQPForm.from_tuples(list(prob))
+        elif isinstance(prob, model.Problem):
+            # the cvxpy-free modelling layer: same extraction and variable order as get_qcqp_form (utilities.py:318-347)
+            self.qcqp_form = model.get_qcqp_form(prob)
+            maximize = prob.objective.NAME == "maximize"
+            self._cvx_vars = prob.variables()
         else:
             self.qcqp_form, maximize = _form_from_cvxpy(prob)
             self._cvx_vars = prob.variables()
@@ -89,11 +96,7 @@ class QCQP:
         self.best_index = b
         self.x = self.X[b].copy()
         if self._cvx_vars is not None:
-            ind = 0
-            for v in self._cvx_vars:
-                size = v.size[0] * v.size[1]
-                v.value = np.reshape(self.x[ind:ind + size], v.size, order='F')
-                ind += size
+            model.assign_vars(self._cvx_vars, self.x)
         return (self._sign(float(f0[b])), float(maxviol[b]))
 
     def set_sdr_solution(self, X, bound=None):
@@ -232,6 +235,11 @@ class QCQP:
             methods = method
         if not all([mm in s.improve_methods for mm in methods]):
             raise Exception("Unknown improve method(s): ", methods)
+        if self._cvx_vars is not None and (self.X is None or self.X.shape[0] == 1) \
+                and all(v.value is not None for v in self._cvx_vars):
+            # single-point mode starts from the variables' current values, as the reference does (flatten_vars, qcqp.py:404),
+            # so a point the user wrote into `x.value` is the one that gets improved
+            self.X = model.flatten_vars(self._cvx_vars, self.n).reshape(1, self.n)
         if self.X is None:
             # the reference means to start from suggest() when no point exists (qcqp.py:427; its test on Variable objects
             # never fires -- SURVEY H7 -- the intent is kept here)

@@ -1,0 +1,222 @@
+"""The cvxpy-free modelling layer (qcqp_b200/model.py): the reference's four example scripts, written
+against it line for line, must extract the same quadratic forms -- same variable order, same constraint order, same relops --
+as the hand-built generators the parity tests use (qcqp_b200/problems.py, pinned by tests/golden/golden.json)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import qcqp_b200.model as cvx
+from qcqp_b200 import problems as pb
+
+
+def _same_forms(form, forms, tol=1e-12):
+    got = form.forms()
+    assert len(got) == len(forms)
+    for j, ((P, q, r, op), (Pw, qw, rw, opw)) in enumerate(zip(got, forms)):
+        assert op == opw, j
+        Pw = sp.csr_matrix(Pw)
+        scale = max(1.0, float(abs(Pw).max()) if Pw.nnz else 0.0)
+        assert abs(P - Pw).max() <= tol * scale, j
+        assert np.allclose(q, qw, rtol=0, atol=tol * max(1.0, np.abs(qw).max())), j
+        assert abs(r - rw) <= tol * max(1.0, abs(rw)), j
+
+
+def test_boolean_least_squares_script():
+    """examples/boolean_least_squares.py:6-15."""
+    n, m = 10, 15
+    np.random.seed(1)
+    A = np.random.randn(m, n)
+    b = np.random.randn(m, 1)
+    x = cvx.Variable(n)
+    obj = cvx.sum_squares(A*x - b)
+    cons = [cvx.square(x) == 1]
+    prob = cvx.Problem(cvx.Minimize(obj), cons)
+    forms, _ = pb.boolean_least_squares(n, m, seed=1)
+    _same_forms(cvx.get_qcqp_form(prob), forms)
+    assert prob.variables() == [x] or [v.id for v in prob.variables()] == [x.id]
+
+
+def test_maxcut_script():
+    """examples/maxcut.py:6-21 (np.matrix adjacency, Maximize, float - expression)."""
+    n = 25
+    np.random.seed(1)
+    p = 0.2
+    W = np.asmatrix(np.random.uniform(low=0.0, high=1.0, size=(n, n)))
+    for i in range(n):
+        W[i, i] = 1
+        for j in range(i+1, n):
+            W[j, i] = W[i, j]
+    W = (W < p).astype(float)
+    x = cvx.Variable(n)
+    obj = 0.25*(cvx.sum_entries(W) - cvx.quad_form(x, W))
+    cons = [cvx.square(x) == 1]
+    prob = cvx.Problem(cvx.Maximize(obj), cons)
+    forms, info = pb.maxcut(n, p, seed=1)
+    assert info["maximize"] and prob.objective.NAME == "maximize"
+    _same_forms(cvx.get_qcqp_form(prob), forms)
+
+
+def test_beamforming_script():
+    """examples/secondary_user_beamforming.py:18-43 (sums of squares of matrix products, `>=` flipped to `<=`)."""
+    n, m, l = 20, 5, 2
+    tau, eta = 20, 2
+    np.random.seed(1)
+    HR = np.random.randn(m, n)
+    HI = np.random.randn(m, n)
+    A = np.hstack((HR, HI))
+    B = np.hstack((-HI, HR))
+    GR = np.random.randn(l, n)
+    GI = np.random.randn(l, n)
+    C = np.hstack((GR, GI))
+    D = np.hstack((-GI, GR))
+    x = cvx.Variable(2*n)
+    obj = cvx.Minimize(cvx.sum_squares(x))
+    cons = [
+        cvx.square(A*x) + cvx.square(B*x) >= tau,
+        cvx.square(C*x) + cvx.square(D*x) <= eta
+    ]
+    prob = cvx.Problem(obj, cons)
+    forms, _ = pb.beamforming(n=n, m=m, l=l, tau=tau, eta=eta, seed=1)
+    _same_forms(cvx.get_qcqp_form(prob), forms)
+
+
+@pytest.mark.parametrize("n", [5, 12])
+def test_circle_packing_script(n):
+    """examples/circle_packing.py:7-17: two variables (the scalar r first, because the objective names it first), matrix
+    variable flattened column-major, scalar promotion in `X >= r` and `X <= B-r`, indexing `X[:, i]`."""
+    X = cvx.Variable(2, n)
+    B = 10
+    r = cvx.Variable()
+    obj = cvx.Maximize(r)
+    cons = [X >= r, X <= B-r, r >= 0]
+    for i in range(n):
+        for j in range(i+1, n):
+            cons.append(cvx.square(2*r) <= cvx.sum_squares(X[:, i]-X[:, j]))
+    prob = cvx.Problem(obj, cons)
+    assert [v.id for v in prob.variables()] == [r.id, X.id]
+    forms, _ = pb.circle_packing(n, B=10.0)
+    form = cvx.get_qcqp_form(prob)
+    assert form.n == 2*n + 1 and form.m == 4*n + 1 + n*(n-1)//2
+    _same_forms(form, forms)
+
+
+def test_values_and_write_back():
+    """assign_vars / flatten_vars (utilities.py:298-316) are column-major per variable and inverse to each other; an
+    expression's value at the variables' values equals the extracted form's."""
+    rs = np.random.RandomState(3)
+    X = cvx.Variable(2, 3)
+    r = cvx.Variable()
+    y = cvx.Variable(4)
+    M = rs.randn(5, 2)
+    expr = cvx.sum_squares(M*X[:, 1] - rs.randn(5, 1)) + 3*cvx.square(r) - cvx.sum_entries(X*rs.randn(3, 2)) + cvx.quad_form(y, rs.randn(4, 4)) + r*y[2]
+    prob = cvx.Problem(cvx.Minimize(expr), [X.T*np.ones((2, 1)) <= y[0:3] + 1, y[3] == 2*r])
+    xs = prob.variables()
+    assert [v.id for v in xs] == [X.id, r.id, y.id]
+    assert expr.value is None
+    v = rs.randn(11)
+    cvx.assign_vars(xs, v)
+    assert X.value.shape == (2, 3) and isinstance(r.value, float) and y.value.shape == (4, 1)
+    assert X.value[1, 2] == v[5] and r.value == v[6] and y.value[0, 0] == v[7]
+    assert np.array_equal(cvx.flatten_vars(xs, 11), v)
+    form = cvx.get_qcqp_form(prob)
+    P, q, c, _ = form.f0.as_tuple()
+    assert abs(expr.value - (v.dot(P.dot(v)) + q.dot(v) + c)) < 1e-10
+    assert form.m == 4 and [f.relop for f in form.fs] == ["<="] * 3 + ["=="]
+    for i, f in enumerate(form.fs[:3]):
+        want = X.value[:, i].sum() - y.value[i, 0] - 1
+        assert abs(v.dot(f.P.dot(v)) + f.qarray.dot(v) + f.r - want) < 1e-12
+    viol = prob.constraints[1].violation
+    assert abs(viol - abs(v[10] - 2*v[6])) < 1e-12
+    cvx.assign_vars(xs, None)
+    assert np.isnan(y.value).all()
+
+
+def test_error_behaviour():
+    x = cvx.Variable(3)
+    with pytest.raises(Exception, match="Objective is not quadratic"):
+        cvx.get_qcqp_form(cvx.Problem(cvx.Minimize(cvx.square(cvx.sum_squares(x)))))
+    with pytest.raises(Exception, match="Not all constraints are quadratic"):
+        cvx.get_qcqp_form(cvx.Problem(cvx.Minimize(cvx.sum_squares(x)), [cvx.square(cvx.square(x)) <= 1]))
+    with pytest.raises(Exception, match="Incompatible dimensions"):
+        np.ones((2, 4))*x
+    with pytest.raises(Exception, match="scalar"):
+        cvx.Minimize(x)
+    with pytest.raises(Exception):
+        bool(x[0] <= 1)
+
+
+# ---- the facade's host logic over the modelling layer, with the engine's pack replaced by the CPU oracle ------------------
+class _OraclePack:
+    """Stands in for engine.Pack in the CPU suite only: same methods, computed by the oracle (test infrastructure)."""
+
+    def __init__(self, forms):
+        from oracle import oracle as orc
+        self._orc, self.P = orc, orc.Problem(forms)
+
+    def eval(self, X):
+        X = np.asarray(X, dtype=np.float64).reshape(-1, self.P.n)
+        return (np.array([self.P.eval(0, x) for x in X]), np.array([self.P.max_violation(x) for x in X]))
+
+    def cd_improve(self, X0, rng, num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, strict=False):
+        import ctypes as C
+        X0 = np.asarray(X0, dtype=np.float64).reshape(-1, self.P.n)
+        X, stats = np.empty_like(X0), []
+        for i in range(X0.shape[0]):
+            st = self._orc.RngState()
+            C.memmove(C.byref(st), C.byref(rng[i]), C.sizeof(st))
+            X[i], s = self.P.improve_cd(X0[i], st, num_iters=num_iters, viol_tol=viol_tol, tol=tol, phase1=phase1, fast=True)
+            C.memmove(C.byref(rng[i]), C.byref(st), C.sizeof(st))
+            stats.append(s)
+        f0, mv = self.eval(X)
+        return X, f0, mv, stats
+
+
+def _golden_cd(golden, name):
+    return [c for c in golden["cd"] if c["name"] == name][0]
+
+
+def test_facade_flows_over_the_model_layer(monkeypatch, golden):
+    """The reference's call sequence QCQP(prob); suggest(RANDOM); improve(COORD_DESCENT) on the goldens G1 and G3 (whose
+    recipe is exactly that sequence), and G2' from a point the user writes into x.value: results, variable write-back,
+    maximize sign and the process-global np.random stream must come out as the reference's own run recorded them."""
+    import qcqp_b200 as Q
+    from qcqp_b200 import engine
+    monkeypatch.setattr(engine, "Pack", _OraclePack)
+
+    # G1: boolean least squares, seed(7); x0 = randn(10); improve_coord_descent
+    g = _golden_cd(golden, "G1")
+    np.random.seed(1)
+    A = np.random.randn(15, 10)
+    b = np.random.randn(15, 1)
+    x = cvx.Variable(10)
+    qc = Q.QCQP(cvx.Problem(cvx.Minimize(cvx.sum_squares(A*x - b)), [cvx.square(x) == 1]))
+    assert not qc.maximize_flag
+    np.random.seed(g["seed"])
+    f_s, v_s = qc.suggest(Q.RANDOM)
+    assert x.value.shape == (10, 1) and np.allclose(x.value.ravel(), g["x0"], rtol=0, atol=0)
+    f, v = qc.improve(Q.COORD_DESCENT)
+    assert abs(f - g["f0"]) <= 1e-9 * abs(g["f0"]) and abs(v - g["maxviol"]) <= 1e-6 * g["maxviol"]
+    assert np.allclose(x.value.ravel(), g["x"], rtol=1e-9, atol=1e-9)
+    assert np.random.get_state()[2] == g["rng"]["pos"]
+
+    # G2': the user supplies the point; phase1=False; the stream is not consumed
+    g = _golden_cd(golden, "G2p")
+    x.value = np.array(g["x0"]).reshape(10, 1)
+    state = np.random.get_state()
+    f, v = qc.improve(Q.COORD_DESCENT, phase1=False)
+    assert abs(f - g["f0"]) <= 1e-9 * abs(g["f0"]) and abs(v - g["maxviol"]) <= 1e-6 * g["maxviol"]
+    assert np.allclose(x.value.ravel(), g["x"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(np.random.get_state()[1], state[1]) and np.random.get_state()[2] == state[2]
+
+    # G3: MAXCUT (Maximize): the returned objective is the cut value, +55.0003...
+    g = _golden_cd(golden, "G3")
+    forms, info = pb.maxcut(25, 0.2, seed=1)
+    W = info["W"]
+    y = cvx.Variable(25)
+    qc = Q.QCQP(cvx.Problem(cvx.Maximize(0.25*(cvx.sum_entries(W) - cvx.quad_form(y, W))), [cvx.square(y) == 1]))
+    assert qc.maximize_flag
+    np.random.seed(g["seed"])
+    qc.suggest(Q.RANDOM)
+    f, v = qc.improve(Q.COORD_DESCENT)
+    assert abs(f + g["f0"]) <= 1e-9 * abs(g["f0"]) and f > 0 and abs(v - g["maxviol"]) <= 1e-6 * g["maxviol"]
+    assert np.random.get_state()[2] == g["rng"]["pos"]

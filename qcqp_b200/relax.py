@@ -69,7 +69,7 @@ def _proj_psd(M):
     return (Q * w) @ Q.T
 
 
-def _admm_sdp(C, A_eq, b_eq, A_le, b_le, iters=20000, mu=1.0, tol=1e-7):
+def _admm_sdp(C, A_eq, b_eq, A_le, b_le, iters=100000, mu=1.0, tol=1e-7):
     """min <C, X>  s.t. <A_eq[i], X> = b_eq[i], <A_le[i], X> <= b_le[i], X >= 0  (all matrices symmetric N x N).
     Dual ADMM (SDPAD); inequalities carry a nonnegative slack.  Returns (X, primal value, info)."""
     N = C.shape[0]
@@ -107,23 +107,24 @@ def _admm_sdp(C, A_eq, b_eq, A_le, b_le, iters=20000, mu=1.0, tol=1e-7):
         z = np.maximum(vz, 0.0)
         sn = (z - vz) / mu
         X, s = Xn, sn
-        if it % 25 == 0:
+        if it % 50 == 0:
             pres = np.linalg.norm(Amat @ X.ravel() + E @ s - bn) / (1.0 + np.linalg.norm(bn))
             dres = np.linalg.norm((Cn - Aty - S).ravel()) / (1.0 + np.linalg.norm(Cn))
             gap = abs(np.sum(Cn * X) - bn @ y) / (1.0 + abs(np.sum(Cn * X)) + abs(bn @ y))
             info = dict(iters=it, pres=float(pres), dres=float(dres), gap=float(gap))
             if max(pres, dres, gap) < tol:
                 break
-            # residual balancing
-            if pres < dres / 10.0:
-                mu /= 1.5
-            elif dres < pres / 10.0:
-                mu *= 1.5
+            # residual balancing (tight: degenerate relaxations such as circle packing otherwise crawl for 10^4 iterations
+            # with the two residuals a constant factor apart)
+            if pres < dres / 2.0:
+                mu /= 2.0
+            elif dres < pres / 2.0:
+                mu *= 2.0
     X = (X + X.T) / 2.0
     return X, float(np.sum(C * X)), info
 
 
-def solve_sdr(form, rank=None, iters=20000, tol=1e-7, seed=0):
+def solve_sdr(form, rank=None, iters=100000, tol=1e-7, seed=0):
     """The SDP relaxation of the QCQP (solve_sdr, qcqp.py:72-97):
         minimize <W0, X>  s.t.  <Wi, X> <= 0 or == 0,  X[-1,-1] = 1,  X >= 0.
     Returns (X*, value)."""
@@ -148,7 +149,7 @@ def solve_sdr(form, rank=None, iters=20000, tol=1e-7, seed=0):
     return X, val
 
 
-def solve_spectral(form, iters=20000, tol=1e-7):
+def solve_spectral(form, iters=100000, tol=1e-7):
     """The spectral relaxation with lambda = 1 (solve_spectral, qcqp.py:41-70): the same lifted SDP with all '<='
     constraints summed into one and all '==' constraints into one.  Returns (x, value) with x the scaled top eigenvector."""
     W0 = homogeneous_form(form.f0)

@@ -44,6 +44,35 @@ def test_no_device_fails_loudly():
         engine.best([1.0], [0.0])
 
 
+def test_c_abi_rejects_bad_arguments():
+    """Error convention of include/qcqp_b200.h: negative status, no exception across the ABI, message through
+    qcqp_last_error.  Argument checks come before any device work, so they can be exercised without a GPU."""
+    from qcqp_b200 import _lib
+    L = _lib.load()
+    INVALID = -1
+    x = (C.c_double * 4)()
+    out = C.c_int32(7)
+    prm = _lib.CdParams(10, 1e-2, 1e-4, 1, 0, 0)
+    calls = {
+        "qcqp_eval": lambda: L.qcqp_eval(None, x, 1, x, x, None),
+        "qcqp_cd_improve": lambda: L.qcqp_cd_improve(None, C.byref(prm), x, 1, x, x, x, x, None),
+        "qcqp_sdr_sample_eval": lambda: L.qcqp_sdr_sample_eval(None, x, x, None, 0, 1, x, x, x),
+        "qcqp_best": lambda: L.qcqp_best(x, x, 0, 1e-4, C.byref(out)),
+        "qcqp_best(null)": lambda: L.qcqp_best(None, x, 4, 1e-4, C.byref(out)),
+        "qcqp_best(tol)": lambda: L.qcqp_best(x, x, 4, 0.0, C.byref(out)),
+        "qcqp_pack_create": lambda: L.qcqp_pack_create(None, C.byref(C.c_void_p())),
+        "qcqp_pack_get_info": lambda: L.qcqp_pack_get_info(None, C.byref(_lib.PackInfo())),
+    }
+    for name, call in calls.items():
+        rc = call()
+        assert rc == INVALID, (name, rc, L.qcqp_last_error())
+        assert L.qcqp_last_error(), name
+    assert out.value == 7                       # outputs untouched on failure
+    L.qcqp_pack_destroy(None)                   # destroying a null handle is a no-op
+    with pytest.raises(Exception, match=r"\[status -1\]"):
+        _lib.check(L.qcqp_best(x, x, 0, 1e-4, C.byref(out)))
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "qcqp_b200")
     for base, _dirs, files in os.walk(pkg):

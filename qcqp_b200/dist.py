@@ -47,6 +47,18 @@ def global_best(bucket, f0, global_index, device=None):
     return bmin, fmin, int(ti.item())
 
 
+def owner_rank(mine, device=None):
+    """The rank that holds the winner: every rank says whether the global best is its own (one MAX all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    t = torch.tensor([dist.get_rank() if mine else -1], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def broadcast_point(x, owner_rank, n, device=None):
     """The winner's x[n] from its owner to every rank (8 n bytes)."""
     import torch

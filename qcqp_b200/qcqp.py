@@ -11,6 +11,7 @@ in QCQPForm.better order; `seed=` gives restart r the MT19937 stream of np.rando
 and no seed the process-global np.random stream is consumed exactly as the reference consumes it.
 """
 import logging
+import sys
 
 import numpy as np
 import scipy.sparse as sp
@@ -20,6 +21,8 @@ from . import engine
 from . import relax
 from . import model
 from .forms import QCQPForm, QuadraticFunction
+
+from . import dist as _dist
 
 log = logging.getLogger("qcqp_b200")   # the reference opens ./qcqp.log at import time (qcqp.py:39); this package does not
 
@@ -53,6 +56,18 @@ def _form_from_cvxpy(prob):
     return QCQPForm(QuadraticFunction(P0, q0, r0), fs), maximize
 
 
+def _process_group():
+    """torch.distributed when a process group of more than one rank is up (one process per GPU under torchrun), else None.
+    torch is only looked at if the caller imported it: the facade itself never needs it."""
+    torch = sys.modules.get("torch")
+    if torch is None:
+        return None
+    d = torch.distributed
+    if d.is_available() and d.is_initialized() and d.get_world_size() > 1:
+        return d
+    return None
+
+
 class QCQP:
     def __init__(self, prob, maximize=False):
         self.prob = prob
@@ -79,7 +94,8 @@ class QCQP:
         self.Sigma = None
         self._F = None
         self.x = None          # current point (the reference keeps it in the cvxpy variables)
-        self.X = None          # current batch [R][n]
+        self.X = None          # current batch [R][n] (under torchrun: this rank's shard of it)
+        self._shard = None     # (lo, hi, total) of this rank's restarts when a batch is sharded over ranks
         self._pack = engine.Pack(self.qcqp_form.forms())
 
     # ---- helpers -----------------------------------------------------------------------------------------
@@ -93,11 +109,34 @@ class QCQP:
         self.batch_f0 = np.asarray([self._sign(v) for v in f0])
         self.batch_maxviol = np.array(maxviol, dtype=np.float64)
         b = engine.best(f0, maxviol) if len(f0) > 1 else 0
+        fb, vb = (float(f0[b]), float(maxviol[b])) if len(f0) else (np.inf, np.inf)
         self.best_index = b
-        self.x = self.X[b].copy()
+        self.x = self.X[b].copy() if len(f0) else np.zeros(self.n)
+        if self._shard is not None:
+            # the only collective -- the best (bucket, f0) over the ranks in `better` order, then the winner's point
+            lo, hi, _total = self._shard
+            per = len(f0) // (hi - lo) if hi > lo else 1          # rows per restart: the number of rho values after an ADMM sweep
+            bucket = int(vb / 1e-4) if len(f0) else np.iinfo(np.int64).max
+            mine = lo * per + b if len(f0) else -1
+            _gb, _gf, gi = _dist.global_best(bucket, fb, mine)
+            owner = _dist.owner_rank(mine == gi and mine >= 0)
+            w = _dist.broadcast_point(np.concatenate([self.x, [fb, vb]]), owner, self.n + 2)
+            self.x, fb, vb = w[:self.n].copy(), float(w[self.n]), float(w[self.n + 1])
+            self.best_index = gi
+            self.best_rank = owner
         if self._cvx_vars is not None:
             model.assign_vars(self._cvx_vars, self.x)
-        return (self._sign(float(f0[b])), float(maxviol[b]))
+        return (self._sign(fb), vb)
+
+    def _shard_of(self, total):
+        """This rank's contiguous slice of a batch of `total` restarts / draws (all of it without a process group)."""
+        d = _process_group()
+        if d is None or total <= 1:
+            self._shard = None
+            return 0, total
+        lo, hi = _dist.shard_range(total, d.get_rank(), d.get_world_size())
+        self._shard = (lo, hi, total)
+        return lo, hi
 
     def set_sdr_solution(self, X, bound=None):
         """Supplies the relaxed solution X* (n+1 x n+1) of solve_sdr (qcqp.py:72-97) computed elsewhere."""
@@ -114,9 +153,13 @@ class QCQP:
         if method not in s.suggest_methods:
             raise Exception("Unknown suggest method: %s\n", method)
         S = int(kwargs.pop("samples", 1))
+        # Under torchrun a batch is sharded: every rank draws the same S points from the (identically seeded) global stream
+        # and keeps its contiguous slice, so the result does not depend on the number of GPUs.
         if method == s.RANDOM:
             X = np.stack([np.random.randn(self.n) for _ in range(S)])
-            f0, mv = self._pack.eval(X)
+            lo, hi = self._shard_of(S)
+            X = X[lo:hi]
+            f0, mv = self._pack.eval(X) if hi > lo else (np.zeros(0), np.zeros(0))
             return self._assign(X, f0, mv)
         if method == s.SPECTRAL:
             if self.spectral_sol is None:
@@ -125,6 +168,7 @@ class QCQP:
                 if self.maximize_flag:
                     self.spectral_bound *= -1
             X = np.asarray(self.spectral_sol, dtype=np.float64).reshape(1, self.n)
+            self._shard = None
             f0, mv = self._pack.eval(X)
             return self._assign(X, f0, mv)
         # SDR
@@ -141,12 +185,19 @@ class QCQP:
                     self.sdr_bound *= -1
         if self.mu is None:
             self.mu, self.Sigma, self._F = engine.sdr_factor(self.sdr_sol, eps=eps, corrected=corrected)
-        if device_rng:
-            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=None, S=S, seed=seed)
+        lo, hi = self._shard_of(S)
+        if hi == lo:
+            X, f0, mv = np.zeros((0, self.n)), np.zeros(0), np.zeros(0)
+            if not device_rng:
+                [np.random.standard_normal(self.n) for _ in range(S)]      # keep the global stream in step with the other ranks
+        elif device_rng:
+            # one Philox stream per rank (seed + rank): unlike the host-stream mode the draws depend on the rank count
+            rank = 0 if self._shard is None else _process_group().get_rank()
+            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=None, S=hi - lo, seed=seed + rank)
         else:
             # np.random.multivariate_normal draws standard_normal(n) per sample from the global stream (SURVEY a-7)
             Z = np.stack([np.random.standard_normal(self.n) for _ in range(S)])
-            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=Z)
+            X, f0, mv = self._pack.sdr_sample_eval(self.mu, self._F, Z=np.ascontiguousarray(Z[lo:hi]))
         return self._assign(X, f0, mv)
 
     def suggest_improve(self, samples=1, seed=0, eps=1e-8, device_rng=False, corrected=False, **kwargs):
@@ -163,12 +214,18 @@ class QCQP:
             self.mu, self.Sigma, self._F = engine.sdr_factor(self.sdr_sol, eps=eps, corrected=corrected)
         fresh = fresh or not getattr(self, "_factor_on_device", False)
         Z = None if device_rng else np.stack([np.random.standard_normal(self.n) for _ in range(S)])
-        seeds = [(int(seed) + r) % (2 ** 32) for r in range(S)]
+        lo, hi = self._shard_of(S)          # under torchrun: this rank's draws, each with the stream of np.random.seed(seed + s)
+        seeds = [(int(seed) + r) % (2 ** 32) for r in range(lo, hi)]
         kw = dict(num_iters=kwargs.get('num_iters', 1000), viol_tol=kwargs.get('viol_tol', 1e-2), tol=kwargs.get('tol', 1e-4),
                   phase1=kwargs.get('phase1', True), strict=kwargs.get('strict', False))
-        res = self._pack.sdr_cd_pipeline(seeds, mu=self.mu if fresh else None, F=self._F if fresh else None, Z=Z, S=S, seed=int(seed), **kw)
+        if hi == lo:
+            self.cd_stats = []
+            return self._assign(np.zeros((0, self.n)), np.zeros(0), np.zeros(0))
+        rank = 0 if self._shard is None else _process_group().get_rank()
+        res = self._pack.sdr_cd_pipeline(seeds, mu=self.mu if fresh else None, F=self._F if fresh else None,
+                                         Z=None if Z is None else np.ascontiguousarray(Z[lo:hi]), S=hi - lo, seed=int(seed) + rank, **kw)
         self._factor_on_device = True
-        for r in range(S):
+        for r in range(hi - lo):
             if res["stats"][r].status == 1:
                 raise ValueError("max() arg is an empty sequence")          # qcqp.py:117
             if res["stats"][r].status == 2:
@@ -180,6 +237,8 @@ class QCQP:
     def _improve(self, method, *args, **kwargs):
         X0 = self.X
         R = X0.shape[0]
+        if R == 0 and method in (s.COORD_DESCENT, s.ADMM):     # a rank whose shard of the batch is empty only joins the best-pick
+            return self._assign(X0, np.zeros(0), np.zeros(0))
         if method == s.COORD_DESCENT:
             seed = kwargs.pop("seed", None)
             kw = dict(num_iters=kwargs.get('num_iters', 1000), viol_tol=kwargs.get('viol_tol', 1e-2), tol=kwargs.get('tol', 1e-4),
@@ -188,7 +247,8 @@ class QCQP:
                 rng = engine.rng_states(states=[np.random.get_state()])   # the reference's process-global stream
             else:
                 base = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
-                rng = engine.rng_states(seeds=[(base + r) % (2 ** 32) for r in range(R)])
+                lo = self._shard[0] if self._shard is not None else 0       # restart r of the whole batch owns stream base + r
+                rng = engine.rng_states(seeds=[(base + lo + r) % (2 ** 32) for r in range(R)])
             X, f0, mv, stats = self._pack.cd_improve(X0, rng, **kw)
             for r in range(R):
                 if stats[r].status == 1:
@@ -235,7 +295,7 @@ class QCQP:
             methods = method
         if not all([mm in s.improve_methods for mm in methods]):
             raise Exception("Unknown improve method(s): ", methods)
-        if self._cvx_vars is not None and (self.X is None or self.X.shape[0] == 1) \
+        if self._cvx_vars is not None and self._shard is None and (self.X is None or self.X.shape[0] == 1) \
                 and all(v.value is not None for v in self._cvx_vars):
             # single-point mode starts from the variables' current values, as the reference does (flatten_vars, qcqp.py:404),
             # so a point the user wrote into `x.value` is the one that gets improved
@@ -245,9 +305,10 @@ class QCQP:
             # never fires -- SURVEY H7 -- the intent is kept here)
             self.suggest(samples=int(kwargs.pop("restarts", 1)))
         restarts = kwargs.pop("restarts", None)
-        if restarts is not None and self.X.shape[0] != int(restarts):
+        held = self._shard[2] if self._shard is not None else self.X.shape[0]
+        if restarts is not None and held != int(restarts):
             raise Exception("restarts=%d but the current batch holds %d points; call suggest(samples=%d) first"
-                            % (int(restarts), self.X.shape[0], int(restarts)))
+                            % (int(restarts), held, int(restarts)))
         for mm in methods:
             f, v = self._improve(mm, *args, **kwargs)
         return (f, v)

@@ -177,6 +177,72 @@ def test_gloo_world_size_2_best_pick(tmp_path):
         assert p.returncode == 0 and "OK %d" % r in o, o
 
 
+_GLOO_FACADE_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import qcqp_b200 as Q
+import qcqp_b200.model as cvx
+from qcqp_b200 import engine, problems as pb
+from qcqp_b200.dist import local_best
+from helpers import OraclePack
+engine.Pack = OraclePack                                   # no GPU here: the facade's host logic over the CPU oracle
+engine.best = lambda f0, mv, tol=1e-4: local_best(f0, mv, tol)[2]
+world = int(sys.argv[4])
+
+def build():
+    np.random.seed(1)
+    A = np.random.randn(18, 12); b = np.random.randn(18, 1)
+    x = cvx.Variable(12)
+    return x, Q.QCQP(cvx.Problem(cvx.Minimize(cvx.sum_squares(A*x - b)), [cvx.square(x) == 1]))
+
+def flow(qc, S):
+    out = []
+    np.random.seed(5)
+    out.append(qc.suggest(Q.RANDOM, samples=S))
+    out.append(qc.improve(Q.COORD_DESCENT, seed=100, num_iters=40))
+    out.append((float(qc.best_index), float(qc.x.sum())))
+    qc.set_sdr_solution(pb.synthetic_sdr_solution(12, rank=3, seed=5))
+    np.random.seed(6)
+    out.append(qc.suggest(Q.SDR, samples=S))
+    out.append(qc.improve(Q.COORD_DESCENT, seed=7, num_iters=40))
+    np.random.seed(8)
+    out.append(qc.suggest_improve(samples=S, seed=300, num_iters=40))
+    out.append((float(qc.best_index), float(qc.x.sum())))
+    return np.array(out)
+
+# single process first: the whole batch on one rank
+x1, q1 = build()
+want = {S: flow(q1, S) for S in (7, 2, 1)}
+x_want = x1.value.copy()
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=world)
+x2, q2 = build()
+for S in (7, 2, 1):                                        # S = 2 < world = 3 leaves a rank with an empty shard; S = 1 is replicated
+    got = flow(q2, S)
+    assert np.array_equal(got, want[S]), (S, got, want[S])
+    if S > 1:
+        lo, hi, total = q2._shard
+        assert total == S and q2.X.shape[0] == hi - lo
+assert np.array_equal(x2.value, x_want)                    # every rank ends with the same written-back point
+dist.barrier(); dist.destroy_process_group()
+print("OK", sys.argv[3])
+'''
+
+
+def test_gloo_sharded_facade_matches_single_process(tmp_path):
+    """SURVEY 8e at the facade: under a process group a batch of restarts / draws is sharded over the ranks and the best point
+    is picked by one reduction; objective, violation, winner index and point must equal the single-process run bit for bit,
+    whatever the number of ranks (restart r always owns the stream seed + r).  Three gloo ranks, the oracle as the pack."""
+    script = tmp_path / "wf.py"
+    script.write_text(_GLOO_FACADE_WORKER)
+    port = str(31600 + (os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(3)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "OK %d" % r in o, o
+
+
 def test_host_relaxations():
     """qcqp_b200/relax.py (host NumPy SDP, setup code): the unit-diagonal mixing method agrees with the general ADMM solver,
     solutions are PSD and feasible, and the values are valid bounds."""

@@ -7,6 +7,7 @@ import scipy.sparse as sp
 
 import qcqp_b200.model as cvx
 from qcqp_b200 import problems as pb
+from helpers import OraclePack
 
 
 def _same_forms(form, forms, tol=1e-12):
@@ -146,31 +147,6 @@ def test_error_behaviour():
 
 
 # ---- the facade's host logic over the modelling layer, with the engine's pack replaced by the CPU oracle ------------------
-class _OraclePack:
-    """Stands in for engine.Pack in the CPU suite only: same methods, computed by the oracle (test infrastructure)."""
-
-    def __init__(self, forms):
-        from oracle import oracle as orc
-        self._orc, self.P = orc, orc.Problem(forms)
-
-    def eval(self, X):
-        X = np.asarray(X, dtype=np.float64).reshape(-1, self.P.n)
-        return (np.array([self.P.eval(0, x) for x in X]), np.array([self.P.max_violation(x) for x in X]))
-
-    def cd_improve(self, X0, rng, num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, strict=False):
-        import ctypes as C
-        X0 = np.asarray(X0, dtype=np.float64).reshape(-1, self.P.n)
-        X, stats = np.empty_like(X0), []
-        for i in range(X0.shape[0]):
-            st = self._orc.RngState()
-            C.memmove(C.byref(st), C.byref(rng[i]), C.sizeof(st))
-            X[i], s = self.P.improve_cd(X0[i], st, num_iters=num_iters, viol_tol=viol_tol, tol=tol, phase1=phase1, fast=True)
-            C.memmove(C.byref(rng[i]), C.byref(st), C.sizeof(st))
-            stats.append(s)
-        f0, mv = self.eval(X)
-        return X, f0, mv, stats
-
-
 def _golden_cd(golden, name):
     return [c for c in golden["cd"] if c["name"] == name][0]
 
@@ -181,7 +157,7 @@ def test_facade_flows_over_the_model_layer(monkeypatch, golden):
     maximize sign and the process-global np.random stream must come out as the reference's own run recorded them."""
     import qcqp_b200 as Q
     from qcqp_b200 import engine
-    monkeypatch.setattr(engine, "Pack", _OraclePack)
+    monkeypatch.setattr(engine, "Pack", OraclePack)
 
     # G1: boolean least squares, seed(7); x0 = randn(10); improve_coord_descent
     g = _golden_cd(golden, "G1")

@@ -196,3 +196,43 @@ def test_facade_flows_over_the_model_layer(monkeypatch, golden):
     f, v = qc.improve(Q.COORD_DESCENT)
     assert abs(f + g["f0"]) <= 1e-9 * abs(g["f0"]) and f > 0 and abs(v - g["maxviol"]) <= 1e-6 * g["maxviol"]
     assert np.random.get_state()[2] == g["rng"]["pos"]
+
+
+def test_model_objects_drive_the_reference_class(monkeypatch, golden):
+    """Build container only (the reference tree is absent on the GPU box): the UNMODIFIED reference `QCQP` class
+    (qcqp.py:367-432) is run on a qcqp_b200.model Problem -- its assign_vars / flatten_vars / prob.variables() /
+    objective.NAME see this package's Variable and Problem objects, only its cvxpy-bound get_qcqp_form is fed the forms
+    extracted here -- and this package's facade must return what it returns, call for call, global stream included."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present")
+    import qcqp_b200 as Q
+    from qcqp_b200 import engine
+    u, q = rh.load()
+    monkeypatch.setattr(engine, "Pack", OraclePack)
+    monkeypatch.setattr(q, "get_qcqp_form", lambda prob: rh.make_form(u, cvx.get_qcqp_form(prob).forms()))
+
+    def problems():
+        np.random.seed(1)
+        A = np.random.randn(15, 10)
+        b = np.random.randn(15, 1)
+        x = cvx.Variable(10)
+        yield x, cvx.Problem(cvx.Minimize(cvx.sum_squares(A*x - b)), [cvx.square(x) == 1]), 7
+        W = pb.maxcut(25, 0.2, seed=1)[1]["W"]
+        y = cvx.Variable(25)
+        yield y, cvx.Problem(cvx.Maximize(0.25*(cvx.sum_entries(W) - cvx.quad_form(y, W))), [cvx.square(y) == 1]), 11
+
+    for var, prob, seed in problems():
+        ref = q.QCQP(prob)
+        np.random.seed(seed)
+        want = [ref.suggest(q.s.RANDOM), ref.improve(q.s.COORD_DESCENT), ref.improve(q.s.COORD_DESCENT, phase1=False)]
+        x_want, state_want = np.array(var.value, dtype=float).copy(), np.random.get_state()
+        var.value = None
+        own = Q.QCQP(prob)
+        np.random.seed(seed)
+        got = [own.suggest(Q.RANDOM), own.improve(Q.COORD_DESCENT), own.improve(Q.COORD_DESCENT, phase1=False)]
+        for (fw, vw), (fg, vg) in zip(want, got):
+            assert abs(fg - fw) <= 1e-9 * abs(fw) and abs(vg - vw) <= 1e-6 * max(abs(vw), 1e-12)
+        assert np.allclose(np.asarray(var.value), x_want.reshape(var.size), rtol=1e-9, atol=1e-9)
+        state = np.random.get_state()
+        assert state[2] == state_want[2] and np.array_equal(state[1], state_want[1])

@@ -62,6 +62,10 @@ class OraclePack:
         f0, mv = self.eval(X)
         return X, f0, mv, stats
 
+    def admm_improve(self, X0, rhos, num_iters=1000, viol_lim=1e4, tol=1e-2, phase1=True):
+        return self.P.improve_admm_batch(X0, np.atleast_1d(rhos), num_iters=num_iters, viol_lim=viol_lim, tol=tol, phase1=phase1,
+                                         nthreads=1)
+
     def sdr_sample_eval(self, mu, F, Z=None, S=None, seed=0):
         X, f0, mv = self.P.sdr_sample_eval(mu, F, np.ascontiguousarray(Z, dtype=np.float64))
         return X, f0, mv

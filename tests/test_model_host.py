@@ -236,3 +236,26 @@ def test_model_objects_drive_the_reference_class(monkeypatch, golden):
         assert np.allclose(np.asarray(var.value), x_want.reshape(var.size), rtol=1e-9, atol=1e-9)
         state = np.random.get_state()
         assert state[2] == state_want[2] and np.array_equal(state[1], state_want[1])
+
+    # golden G4's recipe through both classes: the beamforming script, a start point written into x.value, improve(ADMM, rho)
+    np.random.seed(1)
+    n, m, l = 20, 5, 2
+    HR = np.random.randn(m, n); HI = np.random.randn(m, n)
+    A = np.hstack((HR, HI)); B = np.hstack((-HI, HR))
+    GR = np.random.randn(l, n); GI = np.random.randn(l, n)
+    Cm = np.hstack((GR, GI)); D = np.hstack((-GI, GR))
+    x = cvx.Variable(2*n)
+    prob = cvx.Problem(cvx.Minimize(cvx.sum_squares(x)),
+                       [cvx.square(A*x) + cvx.square(B*x) >= 20, cvx.square(Cm*x) + cvx.square(D*x) <= 2])
+    np.random.seed(4)
+    x0 = 2 * np.random.randn(2*n)
+    ref, own = q.QCQP(prob), Q.QCQP(prob)
+    x.value = x0.reshape(2*n, 1)
+    fw, vw = ref.improve(q.s.ADMM, rho=np.sqrt(m + l))
+    x_want = np.array(x.value, dtype=float).ravel()
+    x.value = x0.reshape(2*n, 1)
+    fg, vg = own.improve(Q.ADMM, rho=np.sqrt(m + l))
+    g4 = golden["admm"][0]
+    assert abs(fw - g4["f0"]) <= 1e-9 * abs(fw), "the reference run here is the one the golden file recorded"
+    assert abs(fg - fw) <= 1e-6 * abs(fw) and abs(vg - vw) <= 1e-6
+    assert np.allclose(np.asarray(x.value).ravel(), x_want, rtol=1e-6, atol=1e-8)

@@ -7,7 +7,8 @@
     qcqp = QCQP(prob)
 
 It replaces, for this path only, what the reference takes from cvxpy 0.4 + CVXcanon (setup.py:11-13, neither vendored):
-`Variable`, `*` / `@` by constants, `+`, `-`, indexing, `square`, `sum_squares`, `quad_form`, `sum_entries`, the relations
+`Variable`, `*` / `@` by constants and between affine expressions, `+`, `-`, indexing, `.T`, `square`, `power(., 2)`, `sum_squares`,
+`quad_form`, `quad_over_lin`, `matrix_frac` (the README's list of quadratic expressions), `sum_entries`, the relations
 `==`, `<=`, `>=`, `Minimize`, `Maximize`, `Problem` -- and the quadratic-coefficient extraction (`QuadCoeffExtractor`) behind
 `get_qcqp_form` (utilities.py:318-347).  Conventions are cvxpy 0.4's: `.size` is the (rows, cols) pair, entries are ordered
 column-major, `a >= b` is the constraint `b - a <= 0`, `prob.variables()` lists variables in order of first appearance
@@ -331,23 +332,39 @@ class _MatMul(Expression):
 
 
 class _Product(Expression):
-    """Product of two scalar affine expressions: (a'x + b)(c'x + d)."""
+    """(affine) * (affine): the matrix product of a (p x k) and a (k x q) affine expression (a scalar factor is promoted),
+    entry (i, j) = sum_l A[i, l] B[l, j] with A[i, l] = a'x + alpha, B[l, j] = b'x + beta."""
 
     def __init__(self, a, b):
-        if not isinstance(b, Expression) or a.size != (1, 1) or b.size != (1, 1):
-            raise Exception("only scalar expressions can be multiplied with each other")
+        if not isinstance(b, Expression):
+            raise Exception("cannot multiply an expression by %s" % type(b))
+        if a.size != (1, 1) and b.size != (1, 1) and a.size[1] != b.size[0]:
+            raise Exception("Incompatible dimensions %s %s" % (a.size, b.size))
         self.args = (a, b)
-        self.size = (1, 1)
+        self.size = b.size if a.size == (1, 1) else a.size if b.size == (1, 1) else (a.size[0], b.size[1])
         self._deg = a._deg + b._deg
 
     def _canon(self, ctx):
-        id_map, N = ctx.id_map, ctx.N
+        N = ctx.N
         a = self.args[0].canon(ctx)
         b = self.args[1].canon(ctx)
         if a.Ps is not None or b.Ps is not None:
             raise Exception("expression is not quadratic")
-        P = a.Q.T.dot(b.Q)
-        return _Coeffs([sp.csr_matrix(P)], a.Q * b.r[0] + b.Q * a.r[0], a.r * b.r)
+        (pa, ka), (kb, qb) = self.args[0].size, self.args[1].size
+        Ps, Qrows, rs = [], [], []
+        for j in range(self.size[1]):
+            for i in range(self.size[0]):
+                if (pa, ka) == (1, 1):              # scalar * matrix: entry (i, j) = a * B[i, j]
+                    ra_, rb_ = [0], [i + j * kb]
+                elif (kb, qb) == (1, 1):            # matrix * scalar
+                    ra_, rb_ = [i + j * pa], [0]
+                else:
+                    ra_, rb_ = [i + l * pa for l in range(ka)], [l + j * kb for l in range(kb)]
+                SA, SB = a.Q[ra_, :], b.Q[rb_, :]
+                Ps.append(sp.csr_matrix(SA.T.dot(SB)))
+                Qrows.append(sp.csr_matrix(SA.T.dot(b.r[rb_]) + SB.T.dot(a.r[ra_])).reshape(1, N))
+                rs.append(float(a.r[ra_].dot(b.r[rb_])))
+        return _Coeffs(Ps, sp.vstack(Qrows, format="csr"), rs)
 
 
 class _Index(Expression):
@@ -468,6 +485,32 @@ def quad_form(x, W):
     if isinstance(W, Expression):
         raise Exception("quad_form needs a constant matrix")
     return _QuadOver(as_expr(x), W)
+
+
+def power(x, p):
+    """power(affine, 2) (README "Quadratic expressions"); p = 1 is the expression itself."""
+    if p == 2:
+        return _Square(as_expr(x))
+    if p == 1:
+        return as_expr(x)
+    raise Exception("power(x, %r) is not quadratic" % (p,))
+
+
+def quad_over_lin(x, y):
+    """sum_squares(x) / y for a constant y > 0."""
+    if isinstance(y, Expression):
+        raise Exception("quad_over_lin needs a constant denominator to stay quadratic")
+    y = float(_const_2d(y)[0, 0])
+    if not y > 0:
+        raise Exception("quad_over_lin needs a positive denominator")
+    return _Scale(_QuadOver(as_expr(x)), 1.0 / y)
+
+
+def matrix_frac(x, P):
+    """x' P^{-1} x for a constant positive definite P."""
+    if isinstance(P, Expression):
+        raise Exception("matrix_frac needs a constant matrix to stay quadratic")
+    return _QuadOver(as_expr(x), np.linalg.inv(_const_2d(P)))
 
 
 def sum_entries(x):

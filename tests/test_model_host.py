@@ -259,3 +259,37 @@ def test_model_objects_drive_the_reference_class(monkeypatch, golden):
     assert abs(fw - g4["f0"]) <= 1e-9 * abs(fw), "the reference run here is the one the golden file recorded"
     assert abs(fg - fw) <= 1e-6 * abs(fw) and abs(vg - vw) <= 1e-6
     assert np.allclose(np.asarray(x.value).ravel(), x_want, rtol=1e-6, atol=1e-8)
+
+
+def test_readme_quadratic_expressions():
+    """The reference README's list of quadratic expressions (README.md "Quadratic expressions"): (affine)*(affine) as a matrix
+    product, power(affine, 2), square, sum_squares, quad_over_lin(affine, constant), matrix_frac(affine, constant),
+    quad_form(affine, constant) -- values of the extracted forms against NumPy."""
+    rs = np.random.RandomState(0)
+    x = cvx.Variable(3); Y = cvx.Variable(2, 3); t = cvx.Variable()
+    A = rs.randn(2, 3); c = rs.randn(3, 1); M = rs.randn(3, 3); Pd = M @ M.T + np.eye(3)
+    xv = rs.randn(3, 1); Yv = rs.randn(2, 3); tv = float(rs.randn())
+    cases = [
+        ((x.T + c.T)*(M*x - c), float(((xv.T + c.T) @ (M @ xv - c))[0, 0])),
+        ((Y + A)*(M*x + c), (Yv + A) @ (M @ xv + c)),
+        (t*(M*x + c), tv * (M @ xv + c)),
+        ((M*x + c)*(t - 2), (M @ xv + c) * (tv - 2)),
+        (cvx.power(A*x - 1, 2), (A @ xv - 1) ** 2),
+        (cvx.quad_over_lin(A*x - 1, 4.0), float(((A @ xv - 1) ** 2).sum() / 4.0)),
+        (cvx.matrix_frac(x - c, Pd), float(((xv - c).T @ np.linalg.inv(Pd) @ (xv - c))[0, 0])),
+        (cvx.quad_form(M*x, Pd) - 2*cvx.sum_squares(Y[1, :]), float(((M @ xv).T @ Pd @ (M @ xv))[0, 0] - 2 * (Yv[1] ** 2).sum())),
+    ]
+    x.value, Y.value, t.value = xv, Yv, tv
+    for e, want in cases:
+        assert e.is_quadratic() and not e.is_affine()
+        assert np.allclose(e.value, want, rtol=1e-12, atol=1e-12)
+    # and through get_qcqp_form: one scalar constraint per entry, column-major
+    prob = cvx.Problem(cvx.Minimize(cases[0][0]), [cases[1][0] <= 1, cases[6][0] == 2])
+    form = cvx.get_qcqp_form(prob)
+    xs = prob.variables()
+    v = cvx.flatten_vars(xs, form.n)
+    vals = [v.dot(f.P.dot(v)) + f.qarray.dot(v) + f.r for f in form.fs]
+    assert form.m == 3 and np.allclose(vals[:2], (cases[1][1] - 1).ravel(order="F")) and abs(vals[2] - (cases[6][1] - 2)) < 1e-12
+    assert not cvx.square(cvx.sum_squares(x)).is_quadratic() and not (cvx.square(x[0])*x[1]).is_quadratic()
+    with pytest.raises(Exception, match="not quadratic"):
+        cvx.power(x, 3)

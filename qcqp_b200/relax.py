@@ -124,8 +124,9 @@ def _admm_sdp(C, A_eq, b_eq, A_le, b_le, iters=100000, mu=1.0, tol=1e-7):
     return X, float(np.sum(C * X)), info
 
 
-def solve_sdr(form, rank=None, iters=100000, tol=1e-7, seed=0):
-    """The SDP relaxation of the QCQP (solve_sdr, qcqp.py:72-97):
+def solve_sdr(form, rank=None, iters=100000, tol=1e-7, seed=0, **_cvxpy_solver_options):
+    """`solver=`, `verbose=` ... of the reference's `prob.solve(*args, **kwargs)` (qcqp.py:92) are accepted and ignored.
+    The SDP relaxation of the QCQP (solve_sdr, qcqp.py:72-97):
         minimize <W0, X>  s.t.  <Wi, X> <= 0 or == 0,  X[-1,-1] = 1,  X >= 0.
     Returns (X*, value)."""
     W0 = homogeneous_form(form.f0)
@@ -149,8 +150,9 @@ def solve_sdr(form, rank=None, iters=100000, tol=1e-7, seed=0):
     return X, val
 
 
-def solve_spectral(form, iters=100000, tol=1e-7):
-    """The spectral relaxation with lambda = 1 (solve_spectral, qcqp.py:41-70): the same lifted SDP with all '<='
+def solve_spectral(form, iters=100000, tol=1e-7, **_cvxpy_solver_options):
+    """(cvxpy solver options are accepted and ignored, as in solve_sdr.)
+    The spectral relaxation with lambda = 1 (solve_spectral, qcqp.py:41-70): the same lifted SDP with all '<='
     constraints summed into one and all '==' constraints into one.  Returns (x, value) with x the scaled top eigenvector."""
     W0 = homogeneous_form(form.f0)
     N = form.n + 1

@@ -109,6 +109,32 @@ def test_coord_descent_goldens(golden, fast):
             assert stats.updates_p1 == 0
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_coord_descent_large_goldens(fast):
+    """The same pin nearer the bench configuration (tests/golden/golden_large.json, make_golden_large.py): runs of the
+    unmodified reference on Boolean LS n = 100 / 150, MAXCUT n = 120 and circle packing with 8 circles."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_large.json")
+    with open(path) as fh:
+        cases = json.load(fh)["cd"]
+    assert len(cases) >= 4
+    for c in cases:
+        forms, _ = forms_of(c)
+        P = orc.Problem(forms)
+        rs = np.random.RandomState(c["seed"])
+        x0 = np.array(c["x0"])
+        rs.standard_normal(len(x0))
+        st = orc.RngState.from_numpy(rs)
+        x, stats = P.improve_cd(x0, st, fast=fast, **c["kwargs"])
+        assert stats.status == 0, c["name"]
+        f0 = P.eval(0, x); mv = P.max_violation(x)
+        assert rel_close(f0, c["f0"], rtol=1e-10, atol=1e-10), (c["name"], f0, c["f0"])
+        assert rel_close(mv, c["maxviol"], rtol=1e-6, atol=1e-9), (c["name"], mv, c["maxviol"])
+        assert rel_close(x, c["x"], rtol=1e-10, atol=1e-10), c["name"]
+        _check_rng(st, c["rng"])
+
+
 def test_better(golden):
     g = golden["better"]
     forms, _ = forms_of(g)

@@ -175,6 +175,33 @@ def test_admm_goldens(golden):
         assert rel_close(P.max_violation(x), c["maxviol"], rtol=1e-6, atol=1e-8), c["name"]
 
 
+def test_admm_c4_reference_runs():
+    """BASELINE configuration C4 at full size (beamforming N=128, 32 constraints): three rho values of the sweep run through the
+    unmodified reference (golden_large.json).  The oracle must reproduce (f0, maxviol) and the number of onecons_qcqp calls, and
+    the oracle fixture the GPU kernels are held to (c4_admm_oracle.json) must carry the same values at those rho."""
+    import json
+    import os
+    from qcqp_b200 import problems as pb
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(gdir, "golden_large.json")) as fh:
+        cases = json.load(fh)["admm"]
+    with open(os.path.join(gdir, "c4_admm_oracle.json")) as fh:
+        fix = json.load(fh)
+    assert len(cases) >= 3
+    forms, _ = pb.beamforming(n=64, m=24, l=8, seed=1)
+    P = orc.Problem(forms)
+    x0 = np.array(fix["x0"])
+    for c in cases:
+        k = c["rho_index"]
+        assert abs(fix["rhos"][k] - c["rho"]) < 1e-12
+        x, st = P.improve_admm(x0, c["rho"])
+        assert st.onecons_calls == c["onecons_calls"], (c["name"], st.onecons_calls, c["onecons_calls"])
+        assert rel_close(P.eval(0, x), c["f0"], rtol=1e-6, atol=1e-9), c["name"]
+        assert rel_close(P.max_violation(x), c["maxviol"], rtol=1e-6, atol=1e-8), c["name"]
+        assert rel_close(fix["f0"][k], c["f0"], rtol=1e-6, atol=1e-9) and rel_close(fix["maxviol"][k], c["maxviol"], rtol=1e-6, atol=1e-8)
+        assert (fix["iters_p1"][k] + fix["iters_p2"][k]) * P.m == c["onecons_calls"]
+
+
 def test_sdr_sampler(golden):
     """np.random.multivariate_normal(mu, Sigma) with the reference's (non-symmetric) Sigma, then eval."""
     from qcqp_b200 import problems as pb

@@ -112,7 +112,8 @@ def test_coord_descent_goldens(golden, fast):
 @pytest.mark.parametrize("fast", [False, True])
 def test_coord_descent_large_goldens(fast):
     """The same pin nearer the bench configuration (tests/golden/golden_large.json, make_golden_large.py): runs of the
-    unmodified reference on Boolean LS n = 100 / 150, MAXCUT n = 120 and circle packing with 8 circles."""
+    unmodified reference on Boolean LS n = 100 / 150, MAXCUT n = 120, circle packing with 8 circles, one restart of the C2 instance
+    (Boolean LS n = 1000: phase 1 and two phase-2 sweeps) and the phase-1 sweep of the C3 instance (MAXCUT n = 2000)."""
     import json
     import os
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_large.json")
@@ -126,7 +127,7 @@ def test_coord_descent_large_goldens(fast):
         x0 = np.array(c["x0"])
         rs.standard_normal(len(x0))
         st = orc.RngState.from_numpy(rs)
-        x, stats = P.improve_cd(x0, st, fast=fast, **c["kwargs"])
+        x, stats = P.improve_cd(x0, st, fast=fast, only_phase=c["only_phase"], **c["kwargs"])
         assert stats.status == 0, c["name"]
         f0 = P.eval(0, x); mv = P.max_violation(x)
         assert rel_close(f0, c["f0"], rtol=1e-10, atol=1e-10), (c["name"], f0, c["f0"])
@@ -202,10 +203,21 @@ def test_admm_c4_reference_runs():
         assert (fix["iters_p1"][k] + fix["iters_p2"][k]) * P.m == c["onecons_calls"]
 
 
-def test_sdr_sampler(golden):
-    """np.random.multivariate_normal(mu, Sigma) with the reference's (non-symmetric) Sigma, then eval."""
+def _large():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_large.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("which", ["small", "c2"])
+def test_sdr_sampler(golden, which):
+    """np.random.multivariate_normal(mu, Sigma) with the reference's (non-symmetric) Sigma, then eval; `c2`: two draws of the
+    reference at n = 1000 (golden_large.json)."""
     from qcqp_b200 import problems as pb
-    for c in golden["sdr"]:
+    cases = golden["sdr"] if which == "small" else _large()["sdr"]
+    assert cases
+    for c in cases:
         forms, _ = pb.boolean_least_squares(**c["gargs"])
         P = orc.Problem(forms)
         Xs = pb.synthetic_sdr_solution(c["n"], rank=c["rank"], seed=c["xs_seed"])

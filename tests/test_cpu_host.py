@@ -271,3 +271,24 @@ def test_host_relaxations():
     X, v = relax.solve_sdr(F)
     assert np.linalg.eigvalsh(X).min() > -1e-7 and abs(X[-1, -1] - 1) < 1e-6
     assert max(np.sum(relax.homogeneous_form(f) * X) for f in F.fs) < 1e-4
+
+
+def test_integration_stub_is_executable_against_the_reference():
+    """INTEGRATION.md's `qcqp/b200.py` (the binding a reference maintainer would add) is run as printed against the unmodified
+    reference's QCQPForm: it must flatten the forms and reach qcqp_pack_create, which -- with no GPU in the build container --
+    answers QCQP_ERR_NO_DEVICE.  Build container only (the reference tree does not travel)."""
+    import torch
+    from oracle import ref_harness as rh
+    from qcqp_b200 import _lib, problems as pb
+    if not rh.available() or torch.cuda.is_available():
+        pytest.skip("needs the reference tree and no GPU")
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# qcqp/b200.py.*?)```", md, re.S).group(1)
+    code = code.replace('C.CDLL("libqcqp_b200.so")', "C.CDLL(%r)" % _lib.LIB_PATH)
+    ns = {}
+    exec(code, ns)
+    u, _q = rh.load()
+    for forms in (pb.boolean_least_squares(10, 15, seed=1)[0], pb.circle_packing(4)[0]):
+        prob = rh.make_form(u, forms)
+        with pytest.raises(Exception, match="no CUDA device"):
+            ns["improve_coord_descent"](np.random.RandomState(0).randn(prob.n), prob)

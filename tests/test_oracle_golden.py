@@ -113,7 +113,8 @@ def test_coord_descent_goldens(golden, fast):
 def test_coord_descent_large_goldens(fast):
     """The same pin nearer the bench configuration (tests/golden/golden_large.json, make_golden_large.py): runs of the
     unmodified reference on Boolean LS n = 100 / 150, MAXCUT n = 120, circle packing with 8 circles, one restart of the C2 instance
-    (Boolean LS n = 1000: phase 1 and two phase-2 sweeps) and the phase-1 sweep of the C3 instance (MAXCUT n = 2000)."""
+    (Boolean LS n = 1000: phase 1 and two phase-2 sweeps) and the phase-1 sweeps of the C3 instance (MAXCUT n = 2000) and of the
+    C5 instance (circle packing, 200 circles: N = 401, 20 701 constraints)."""
     import json
     import os
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_large.json")

@@ -72,6 +72,8 @@ def main():
         ("circle8", "circle", dict(ncirc=8), "randn", 64, dict(num_iters=5)),
         # the bench configuration C2 itself: phase 1 and two phase-2 sweeps of one restart (~2 min per sweep in the reference)
         ("bls1000_2sweeps", "bls", dict(n=1000, m=1500, seed=1), "randn", 71, dict(num_iters=2)),
+        # ... and one restart of it run to convergence (num_iters = 1000: about 20 phase-2 sweeps)
+        ("bls1000_full", "bls", dict(n=1000, m=1500, seed=1), "randn", 74, {}),
         # C3's instance (MAXCUT n = 2000, p = 0.1, CSR objective): the phase-1 sweep of one restart (~10 min in the reference)
         ("maxcut2000_p1", "maxcut", dict(n=2000, p=0.1, seed=1), "randn", 72, dict(num_iters=1), 1),
         # C5's instance (circle packing, 200 circles: N = 401, 20 701 constraints): the first phase-1 sweep of one restart

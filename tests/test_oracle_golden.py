@@ -204,6 +204,25 @@ def test_admm_c4_reference_runs():
         assert (fix["iters_p1"][k] + fix["iters_p2"][k]) * P.m == c["onecons_calls"]
 
 
+def test_admm_c4_whole_sweep_fixture_equals_the_reference():
+    """All 16 rho values of C4's sweep, run through the unmodified reference (c4_admm_reference.json, 1-25 s each): the oracle
+    fixture the GPU ADMM kernels are tested against (c4_admm_oracle.json) carries the reference's (f0, maxviol) to 1e-9 and its
+    exact number of onecons_qcqp calls at every rho."""
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(gdir, "c4_admm_reference.json")) as fh:
+        runs = json.load(fh)["runs"]
+    with open(os.path.join(gdir, "c4_admm_oracle.json")) as fh:
+        fix = json.load(fh)
+    assert sorted(c["rho_index"] for c in runs) == list(range(16))
+    for c in runs:
+        k = c["rho_index"]
+        assert abs(fix["rhos"][k] - c["rho"]) < 1e-12
+        assert rel_close(fix["f0"][k], c["f0"], rtol=1e-9, atol=0) and rel_close(fix["maxviol"][k], c["maxviol"], rtol=1e-6, atol=1e-9)
+        assert (fix["iters_p1"][k] + fix["iters_p2"][k]) * 32 == c["onecons_calls"], k
+
+
 def _large():
     import json
     import os

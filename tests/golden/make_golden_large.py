@@ -76,6 +76,8 @@ def main():
         ("bls1000_full", "bls", dict(n=1000, m=1500, seed=1), "randn", 74, {}),
         # C3's instance (MAXCUT n = 2000, p = 0.1, CSR objective): the phase-1 sweep of one restart (~10 min in the reference)
         ("maxcut2000_p1", "maxcut", dict(n=2000, p=0.1, seed=1), "randn", 72, dict(num_iters=1), 1),
+        # ... and phase 1 followed by one phase-2 sweep (the exact-zero tests of SURVEY H5 at n = 2000)
+        ("maxcut2000_1sweep_each", "maxcut", dict(n=2000, p=0.1, seed=1), "randn", 72, dict(num_iters=1)),
         # C5's instance (circle packing, 200 circles: N = 401, 20 701 constraints): the first phase-1 sweep of one restart
         ("circle200_p1", "circle", dict(ncirc=200), "randn", 73, dict(num_iters=1), 1),
     ]

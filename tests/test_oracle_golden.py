@@ -122,8 +122,9 @@ def test_coord_descent_large_goldens(fast):
         cases = json.load(fh)["cd"]
     assert len(cases) >= 4
     for c in cases:
-        if not fast and c["name"] == "bls1000_full":
-            continue        # the faithful mode's O(n nnz) per step is held to the reference at this size by bls1000_2sweeps
+        if not fast and c["name"] in ("bls1000_full", "maxcut2000_1sweep_each"):
+            continue        # the faithful mode's O(n nnz) per step is held to the reference at these sizes by bls1000_2sweeps and
+                            # maxcut2000_p1 (the two skipped runs take it a minute each; checked once by hand when they were minted)
         forms, _ = forms_of(c)
         P = orc.Problem(forms)
         rs = np.random.RandomState(c["seed"])

@@ -167,6 +167,12 @@ int qcqp_cd_improve_device(qcqp_pack* pack, const qcqp_cd_params* params, const 
  * the separable dense-objective path (the only one split into launches), else 0.  Call after synchronising the stream. */
 int qcqp_cd_get_timing(qcqp_pack* pack, double* ms /*[4]*/, int32_t* count);
 
+/* Device counters of the last qcqp_cd_improve* call (zeroed at its start; kernels that do not count leave zeros):
+ * out[0] rows of P_0 applied to the cached g = P_0 x (one per accepted phase-2 move), out[1] 32 x 32 diagonal blocks of P_0
+ * staged by TMA, out[2] rows read by from-scratch refreshes of g, out[3] bytes the phase-2 kernel requested from L2.
+ * *count = 4.  Call after synchronising the stream.  bench.py derives the L2 roofline of the phase-2 kernel from out[3]. */
+int qcqp_cd_get_counters(qcqp_pack* pack, uint64_t* out /*[4]*/, int32_t* count);
+
 /* ---- consensus ADMM: improve_admm(x0, prob, rho=...) for K rho values x R starts
  *      (qcqp.py:254-285 -> admm_phase1 :195-212, admm_phase2 :215-251, onecons_qcqp utilities.py:149-196,
  *       QCQPForm.better :135-146).
@@ -209,6 +215,13 @@ int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* params, const do
 int qcqp_best(const double* f0, const double* maxviol, int32_t R, double tol, int32_t* best_idx);
 int qcqp_best_device(const double* df0, const double* dmaxviol, int32_t R, double tol, int32_t* dbest_idx,
                      int64_t* dbest_bucket, double* dbest_f0, void* stream);
+
+/* ---- measurement helpers (no counterpart in the reference): the ceilings bench.py reports its roofline fractions against,
+ *      measured on the device that is current, with CUDA events.  The path is FP64 and its matrices are L2-resident, so the
+ *      driver's HBM-copy / bf16-GEMM peaks do not bound it. ------------------------------------------------------------- */
+int qcqp_probe_l2_bandwidth(int64_t bytes /* buffer size, must stay L2-resident (e.g. 32 MiB) */, int32_t iters,
+                            double* gb_per_s /* sustained L2 -> SM read bandwidth */);
+int qcqp_probe_fp64_peaks(double* dmma_tflops /* mma.sync.m8n8k4.f64 from registers */, double* dfma_tflops /* FMA pipe */);
 
 #ifdef __cplusplus
 }

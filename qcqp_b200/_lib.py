@@ -67,6 +67,7 @@ EXPORTS = {
     "qcqp_cd_improve_device": (C.c_int, [C.c_void_p, C.POINTER(CdParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qcqp_cd_get_timing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcqp_cd_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qcqp_admm_pack_eig": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qcqp_admm_improve": (C.c_int, [C.c_void_p, C.POINTER(AdmmParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -81,6 +82,8 @@ EXPORTS = {
                                        C.c_void_p, C.c_void_p]),
     "qcqp_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "qcqp_best_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcqp_probe_l2_bandwidth": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
+    "qcqp_probe_fp64_peaks": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

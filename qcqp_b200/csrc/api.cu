@@ -150,6 +150,20 @@ extern "C" int qcqp_cd_get_timing(qcqp_pack* pack, double* ms, int32_t* count)
     return QCQP_OK;
 }
 
+// Device counters of the last qcqp_cd_improve* call on this pack (zeroed at its start; kernels that do not count leave zeros):
+// out[0] rows of P_0 applied to g (accepted phase-2 moves), out[1] 32 x 32 diagonal blocks fetched, out[2] rows read by
+// from-scratch refreshes of g, out[3] bytes requested from L2 by the phase-2 kernel.  Call after synchronising the stream.
+extern "C" int qcqp_cd_get_counters(qcqp_pack* pack, uint64_t* out, int32_t* count)
+{
+    TRY(check_pack(pack, "qcqp_cd_get_counters"));
+    if (!out || !count) return fail(QCQP_ERR_INVALID, "qcqp_cd_get_counters: null argument");
+    *count = 0;
+    if (!pack->d_ctr) return QCQP_OK;
+    QCQP_CUDA_TRY(cudaMemcpy(out, pack->d_ctr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *count = 4;
+    return QCQP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int qcqp_admm_improve_device(qcqp_pack* pack, const qcqp_admm_params* params, const double* drhos, const double* dZinv,
                                         int32_t K, const double* dX0, int32_t R, double* dX, double* df0, double* dmaxviol,

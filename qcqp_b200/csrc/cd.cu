@@ -962,6 +962,7 @@ int cd_launch(qcqp_pack* p, const qcqp_cd_params* prm, const double* dX0, int R,
               double* dmv, qcqp_cd_stats* dstats, cudaStream_t stream)
 {
     if (R <= 0) return QCQP_OK;
+    if (p->d_ctr) QCQP_CUDA_TRY(cudaMemsetAsync(p->d_ctr, 0, 8 * sizeof(unsigned long long), stream));
     CdLayout L;
     // CTA-per-restart kernel (cd_blk.cu): sparse problems whose coordinates meet many constraints; strict = 4 / 5 force it
     // (fast / strict summation) for A/B runs and the parity tests at small sizes

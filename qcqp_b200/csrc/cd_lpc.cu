@@ -15,6 +15,8 @@
 //    number) are committed wholesale, that one is applied (g += delta * column k: the only time a row of P_0 is read), and
 //    the pass restarts after it.  On Boolean LS ~3% of the steps move.
 // The objective's row dot comes from the cached g = P_0 x: (P_0 z)_k = g_k - P_0[k,k] x_k.
+#include <cstdlib>
+
 #include "cd_shared.cuh"
 #include "common.cuh"
 #include "onevar.cuh"
@@ -673,8 +675,16 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
         rc = gemm_plain_launch(R, n, n, dX, n, p->v.dense_P, p->v.ld, G, npad, stream);
         if (rc != QCQP_OK) return rc;
         QCQP_CUDA_TRY(cudaEventRecord(p->ev[2], stream));
-        cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 2, dX0, R, drng, dX, G, df0, dmv, stats);
-        QCQP_CUDA_TRY(cudaGetLastError());
+        // phase 2: the resolver / helper kernel with TMA-staged diagonal blocks (cd_lpc2.cu); QCQP_LPC2=0 keeps the one-warp kernel
+        // of round 1 for A/B runs (bit-identical results)
+        const char* e2 = getenv("QCQP_LPC2");
+        if (lpc2_supported(n) && !(e2 && e2[0] == '0')) {
+            rc = lpc2_launch(p, k, R, drng, dX, G, stats, stream);
+            if (rc != QCQP_OK) return rc;
+        } else {
+            cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 2, dX0, R, drng, dX, G, df0, dmv, stats);
+            QCQP_CUDA_TRY(cudaGetLastError());
+        }
         QCQP_CUDA_TRY(cudaEventRecord(p->ev[3], stream));
         rc = eval_launch(p, dX, R, df0, dmv, nullptr, stream);
         if (rc != QCQP_OK) return rc;

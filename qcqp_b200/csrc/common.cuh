@@ -88,6 +88,7 @@ struct LpcView {
     const int* o_rbeg;     // [n] objective row k (off-diagonal) in row_col/row_val; unused when the objective is dense
     const int* o_rlen;     // [n]
     const unsigned char* o_inc;  // [n] 1 when the objective involves x_k structurally
+    const double* cst6;    // [n][6] (c_p, c_q, c_r, c_rel, o_diag, o_q) of coordinate k side by side (cd_lpc2.cu stages them by TMA)
     double o_r;
     int obj_dense;
 };
@@ -121,6 +122,12 @@ struct qcqp_pack {
     cudaEvent_t ev[6];
     bool ev_ok;
     int ev_count;
+    // TMA tensor map of the dense objective matrix (CUtensorMap, built on first use by cd_lpc2.cu): 0 not built, 1 ok, -1 failed
+    alignas(64) unsigned char tmap[128];
+    int tmap_state;
+    // device counters of the last qcqp_cd_improve* call (qcqp_cd_get_counters): [0] rows of P_0 applied, [1] diagonal blocks
+    // fetched, [2] rows read by from-scratch refreshes, [3] bytes requested from L2, [4..7] reserved
+    unsigned long long* d_ctr;
 };
 
 namespace qcqp {

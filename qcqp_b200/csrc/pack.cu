@@ -272,7 +272,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     std::memset(&p->v, 0, sizeof(p->v));
     std::memset(&p->info, 0, sizeof(p->info));
     p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->ws2 = nullptr; p->ws2_bytes = 0; p->has_eig = false; p->lpc_ok = false; p->sdr_mu = nullptr; p->sdr_F = nullptr; p->sdr_ok = false;
-    p->ev_ok = false; p->ev_count = 0;
+    p->ev_ok = false; p->ev_count = 0; p->tmap_state = 0; p->d_ctr = nullptr;
     std::memset(&p->lpc, 0, sizeof(p->lpc));
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;
@@ -291,6 +291,12 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     UP(q_ptr, q_ptr); UP(q_idx, q_idx); UP(q_val, q_val);
     UP(r, r); UP(relop, relop); UP(dense_slot, dense_slot); UP(dense_form, dense_form); UP(dense_P, dense_P);
 #undef UP
+    if (rc == QCQP_OK) {
+        std::vector<unsigned long long> zero8(8, 0ull);
+        const unsigned long long* dc = nullptr;
+        rc = upload(p, zero8, &dc);
+        p->d_ctr = const_cast<unsigned long long*>(dc);
+    }
     if (rc != QCQP_OK) { qcqp_pack_destroy(p); return rc; }
 
     // ---- separable view for the lane-per-coordinate kernel (cd_lpc.cu) ----------------------------------------
@@ -334,6 +340,15 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
             if (rc == QCQP_OK) rc = upload(p, o_rbeg, &L.o_rbeg);
             if (rc == QCQP_OK) rc = upload(p, o_rlen, &L.o_rlen);
             if (rc == QCQP_OK) rc = upload(p, o_inc, &L.o_inc);
+            {
+                // the six per-coordinate constants side by side (48 B per coordinate): one bulk copy stages a pass's worth
+                std::vector<double> cst6((size_t)n * 6);
+                for (int k = 0; k < n; k++) {
+                    double* c = &cst6[(size_t)k * 6];
+                    c[0] = c_p[k]; c[1] = c_q[k]; c[2] = c_r[k]; c[3] = (double)c_rel[k]; c[4] = o_diag[k]; c[5] = o_q[k];
+                }
+                if (rc == QCQP_OK) rc = upload(p, cst6, &L.cst6);
+            }
             if (rc != QCQP_OK) { qcqp_pack_destroy(p); return rc; }
         }
         p->lpc_ok = ok;

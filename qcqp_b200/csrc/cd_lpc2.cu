@@ -6,8 +6,8 @@
 //   warp 0, the RESOLVER, owns the serial chain of one-variable decisions (get_onevar_func utilities.py:99-105 through the
 //           cached g = P_0 x, onevar_qcqp :241-288 on the memoised pieces; in the common case a certified threshold test on g_k,
 //           see "certified classification" below).  Its loop is branch-free SIMD work plus one ballot and two shuffles per
-//           move; everything else is POSTED as a command (two shared-memory stores and an mbarrier arrive by all 32 lanes, no
-//           election, no fence): "row k moved by delta", "publish g of block b", "stage the block and constants of pass kk".
+//           move; everything else is POSTED as a command (two shared-memory stores by lane 0 and an mbarrier arrive by all 32 lanes,
+//           no fence): "row k moved by delta", "publish g of block b", "stage the block and constants of pass kk".
 //   warp 1, the COPY warp, turns commands into TMA traffic: for a move, a bulk copy (cp.async.bulk) of the moved row of P_0 into
 //           a ring of S row slots in shared memory; for a stage command, the 32 x 32 diagonal block of P_0 (one
 //           cp.async.bulk.tensor.2d box) and the 48 bytes of constants of each of its coordinates.  Up to S rows are in flight
@@ -225,11 +225,11 @@ cd_lpc2_kernel(const __grid_constant__ CUtensorMap tmapD, PackView P, LpcView V,
     unsigned long long c_rows = 0, c_blk = 0, c_ref = 0;
     long long pt_drain = 0, pt_mbar = 0, pt_res = 0, pt_pro = 0, pt_a = 0, pt_b = 0, pt_cls = 0, pt_push = 0, pt_c = 0;
     const long long pt_begin = prof ? clock64() : 0;
-    // command queue producer state (warp-uniform).  A command is posted by ALL lanes: the same two words, then 32 arrivals.
+    // command queue producer state (warp-uniform).  A command is two words stored by lane 0 (predicated, no branch) and an arrive
+    // by ALL 32 lanes: no election, no fence; the phase completes with lane 0's own arrive, which follows its stores.
     int ce = 0;
     auto post = [&](int cmd, double delta) {
-        w.cq_cmd[ce] = cmd;
-        w.cq_dl[ce] = delta;
+        if (lane == 0) { w.cq_cmd[ce] = cmd; w.cq_dl[ce] = delta; }
         mbar_arrive(&w.cfull[ce]);
         ce = (ce + 1 == CQ) ? 0 : ce + 1;
     };

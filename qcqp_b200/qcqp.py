@@ -102,28 +102,65 @@ class QCQP:
     def _sign(self, f):
         return -f if self.maximize_flag else f
 
+    _STATUS_ERRORS = {1: (ValueError, "max() arg is an empty sequence"),          # qcqp.py:117
+                      2: (OverflowError, "Range exceeds valid bounds")}           # utilities.py:267
+
+    def _mask_failed(self, f0, maxviol, stats):
+        """A restart whose kernel status mirrors a Python exception of the reference.  A single point in a single process raises
+        at once, as the reference does.  In a batch (or under torchrun) a failed restart must neither throw the other results
+        away nor leave the other ranks waiting in the best-pick collective: it is marked (+inf, +inf) so that it cannot win, and
+        _assign raises -- on every rank, after the collective -- only if every restart of the whole batch failed."""
+        bad = [r for r in range(len(stats)) if stats[r].status != 0]
+        self._fail_code = stats[bad[0]].status if bad else 0
+        self._fail_count = len(bad)
+        if bad and len(stats) == 1 and self._shard is None:
+            exc, msg = self._STATUS_ERRORS.get(self._fail_code, (Exception, "restart failed with status %d" % self._fail_code))
+            raise exc(msg)
+        if bad:
+            f0 = np.array(f0, dtype=np.float64, copy=True); maxviol = np.array(maxviol, dtype=np.float64, copy=True)
+            f0[bad] = np.inf; maxviol[bad] = np.inf
+        return f0, maxviol
+
     def _assign(self, X, f0, maxviol):
         """Keeps the batch, selects the best point (QCQPForm.better order) and writes it back (assign_vars,
         utilities.py:298-308, column-major per variable)."""
         self.X = np.array(X, dtype=np.float64).reshape(-1, self.n)
         self.batch_f0 = np.asarray([self._sign(v) for v in f0])
         self.batch_maxviol = np.array(maxviol, dtype=np.float64)
-        b = engine.best(f0, maxviol) if len(f0) > 1 else 0
-        fb, vb = (float(f0[b]), float(maxviol[b])) if len(f0) else (np.inf, np.inf)
+        fail_count, fail_code = getattr(self, "_fail_count", 0), getattr(self, "_fail_code", 0)
+        self._fail_count = self._fail_code = 0
+        f0a = np.asarray(f0, dtype=np.float64); mva = np.asarray(maxviol, dtype=np.float64)
+        usable = np.isfinite(f0a) & ~np.isnan(mva) if len(f0a) else np.zeros(0, dtype=bool)
+        if usable.any():
+            fsel = np.where(usable, f0a, np.inf); vsel = np.where(usable, mva, np.inf)
+            b = engine.best(fsel, vsel) if len(f0a) > 1 else 0
+            fb, vb = float(f0a[b]), float(mva[b])
+        else:
+            b, fb, vb = -1, np.inf, np.inf
         self.best_index = b
-        self.x = self.X[b].copy() if len(f0) else np.zeros(self.n)
+        self.x = self.X[b].copy() if b >= 0 else np.zeros(self.n)
+        total, failed = len(f0a), fail_count
         if self._shard is not None:
-            # SURVEY 8e: the only collective -- the best (bucket, f0) over the ranks in `better` order, then the winner's point
+            # SURVEY 8e: the only collective -- ONE all-gather carrying each rank's best (bucket, f0, index), its point, and its
+            # counts of restarts / failed restarts; every rank then takes the same pick in the `better` order
             lo, hi, _total = self._shard
-            per = len(f0) // (hi - lo) if hi > lo else 1          # rows per restart: the number of rho values after an ADMM sweep
-            bucket = int(vb / 1e-4) if len(f0) else np.iinfo(np.int64).max
-            mine = lo * per + b if len(f0) else -1
-            _gb, _gf, gi = _dist.global_best(bucket, fb, mine)
-            owner = _dist.owner_rank(mine == gi and mine >= 0)
-            w = _dist.broadcast_point(np.concatenate([self.x, [fb, vb]]), owner, self.n + 2)
-            self.x, fb, vb = w[:self.n].copy(), float(w[self.n]), float(w[self.n + 1])
+            per = len(f0a) // (hi - lo) if hi > lo else 1          # rows per restart: the number of rho values after an ADMM sweep
+            bucket = int(vb / 1e-4) if (b >= 0 and np.isfinite(vb)) else np.iinfo(np.int64).max
+            mine = lo * per + b if b >= 0 else -1
+            d = _process_group()
+            payload = np.concatenate([self.x, [fb, vb, float(d.get_rank()), float(total), float(failed), float(fail_code)]])
+            _gb, _gf, gi, w = _dist.global_best(bucket, fb, mine, x=payload)
+            counts = _dist.last_gather_columns(self.n + 3, 3)        # (restarts, failed, first failure code) of every rank
+            total, failed = int(counts[:, 0].sum()), int(counts[:, 1].sum())
+            codes = counts[:, 2][counts[:, 2] > 0]
+            fail_code = int(codes[0]) if len(codes) else 0
+            if w is not None:
+                self.x, fb, vb = w[:self.n].copy(), float(w[self.n]), float(w[self.n + 1])
+                self.best_rank = int(w[self.n + 2])
             self.best_index = gi
-            self.best_rank = owner
+        if total > 0 and failed >= total:
+            exc, msg = self._STATUS_ERRORS.get(fail_code, (Exception, "every restart failed (status %d)" % fail_code))
+            raise exc(msg)
         if self._cvx_vars is not None:
             model.assign_vars(self._cvx_vars, self.x)
         return (self._sign(fb), vb)
@@ -225,37 +262,36 @@ class QCQP:
         res = self._pack.sdr_cd_pipeline(seeds, mu=self.mu if fresh else None, F=self._F if fresh else None,
                                          Z=None if Z is None else np.ascontiguousarray(Z[lo:hi]), S=hi - lo, seed=int(seed) + rank, **kw)
         self._factor_on_device = True
-        for r in range(hi - lo):
-            if res["stats"][r].status == 1:
-                raise ValueError("max() arg is an empty sequence")          # qcqp.py:117
-            if res["stats"][r].status == 2:
-                raise OverflowError("Range exceeds valid bounds")           # utilities.py:267
         self.cd_stats = res["stats"]
-        return self._assign(res["X"], res["f0"], res["maxviol"])
+        f0m, mvm = self._mask_failed(res["f0"], res["maxviol"], res["stats"])
+        return self._assign(res["X"], f0m, mvm)
 
     # ---- improve (qcqp.py:403-432) -----------------------------------------------------------------------
     def _improve(self, method, *args, **kwargs):
         X0 = self.X
         R = X0.shape[0]
+        cd_base = None
+        if method == s.COORD_DESCENT:
+            # under torchrun every rank must consume the identically seeded global stream identically: the base seed is drawn
+            # BEFORE the empty-shard return, and a sharded run never reads or overwrites the global state per rank
+            seed = kwargs.pop("seed", None)
+            single_stream = seed is None and R == 1 and self._shard is None
+            if not single_stream:
+                cd_base = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
         if R == 0 and method in (s.COORD_DESCENT, s.ADMM):     # a rank whose shard of the batch is empty only joins the best-pick
             return self._assign(X0, np.zeros(0), np.zeros(0))
         if method == s.COORD_DESCENT:
-            seed = kwargs.pop("seed", None)
             kw = dict(num_iters=kwargs.get('num_iters', 1000), viol_tol=kwargs.get('viol_tol', 1e-2), tol=kwargs.get('tol', 1e-4),
                       phase1=kwargs.get('phase1', True), strict=kwargs.get('strict', False))
-            if seed is None and R == 1:
+            if single_stream:
                 rng = engine.rng_states(states=[np.random.get_state()])   # the reference's process-global stream
             else:
-                base = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+                base = cd_base
                 lo = self._shard[0] if self._shard is not None else 0       # restart r of the whole batch owns stream base + r
                 rng = engine.rng_states(seeds=[(base + lo + r) % (2 ** 32) for r in range(R)])
             X, f0, mv, stats = self._pack.cd_improve(X0, rng, **kw)
-            for r in range(R):
-                if stats[r].status == 1:
-                    raise ValueError("max() arg is an empty sequence")          # qcqp.py:117
-                if stats[r].status == 2:
-                    raise OverflowError("Range exceeds valid bounds")           # utilities.py:267
-            if seed is None and R == 1:
+            f0, mv = self._mask_failed(f0, mv, stats)
+            if single_stream:
                 np.random.set_state(engine.rng_state_tuple(rng[0]))
             self.cd_stats = stats
             return self._assign(X, f0, mv)

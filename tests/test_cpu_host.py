@@ -160,6 +160,12 @@ assert (gb, gf, gi) == want, ((gb, gf, gi), want)
 owner = 0 if gi < shard_range(R, 0, 2)[1] else 1
 x = broadcast_point(X[gi] if rank == owner else np.zeros(n), owner, n)
 assert np.array_equal(x, X[gi])
+# the same pick with the winner's point riding on the single all-gather
+gb2, gf2, gi2, xw = global_best(b, f, lo + i if i >= 0 else -1, x=X[lo + i])
+assert (gb2, gf2, gi2) == want and np.array_equal(xw, X[gi])
+# a rank with nothing to offer (empty shard / every restart failed) cannot win and does not hang the others
+e = global_best(np.iinfo(np.int64).max, np.inf, -1, x=np.zeros(n)) if rank == 1 else global_best(b, f, lo + i, x=X[lo + i])
+assert e[2] == shard_range(R, 0, 2)[0] + local_best(f0[:shard_range(R, 0, 2)[1]], mv[:shard_range(R, 0, 2)[1]])[2]
 dist.barrier(); dist.destroy_process_group()
 print("OK", rank)
 '''
@@ -292,3 +298,46 @@ def test_integration_stub_is_executable_against_the_reference():
         prob = rh.make_form(u, forms)
         with pytest.raises(Exception, match="no CUDA device"):
             ns["improve_coord_descent"](np.random.RandomState(0).randn(prob.n), prob)
+
+
+def test_reference_window_runner_and_clean_cpu_arm(tmp_path):
+    """bench.py's CPU arms: (i) oracle/ref_python.py times windows of the UNMODIFIED reference's coord_descent_phase2 (here from
+    /root/reference or baseline/_ref, whichever exists) and counts exactly the coordinate steps asked for; (ii) building a
+    benchmark instance and running the C port does not import qcqp_b200 nor map libqcqp_b200.so (the reference arm's record
+    must be free of the product library)."""
+    from oracle import ref_python as rp
+    if rp.ref_root() is None:
+        pytest.skip("reference package not present (neither baseline/_ref nor /root/reference)")
+    pool = rp.ReferencePool("boolean_least_squares", dict(n=40, m=60, seed=1), procs=2)
+    steps, wall, secs = pool.window(5)
+    pool.close()
+    assert steps == 10 and wall > 0 and len(secs) == 2
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import bench
+cfg = dict(bench.CONFIGS["c2"]); cfg["gargs"] = dict(n=24, m=36, seed=1)
+forms, info, Xstar = bench.build_problem(cfg)
+wk, dt = bench.port_sample(cfg, forms, Xstar, 8, 2)
+assert wk > 0
+assert not any(m == "qcqp_b200" or m.startswith("qcqp_b200.") for m in sys.modules), [m for m in sys.modules if "qcqp" in m]
+assert "libqcqp_b200" not in open("/proc/self/maps").read()
+print("CLEAN")
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "CLEAN" in out.stdout, out.stdout + out.stderr
+
+
+def test_bench_strong_scaling_shards_partition_one_batch():
+    """bench.py c3 / c5: the per-rank inputs of a strong-scaling run are slices of ONE batch (same draws, same seeds whatever N)."""
+    import bench
+    cfg = dict(bench.CONFIGS["c3"]); cfg["gargs"] = dict(n=12, p=0.3, seed=1); cfg["restarts"] = 10
+    forms, _i, _x = bench.build_problem(cfg, want_sdr=False)
+    whole, seeds = bench.starts_for(cfg, forms, None, 0, 10, 0, False)
+    parts = [bench.starts_for(cfg, forms, None, *bench.shard(10, r, 4), r, False) for r in range(4)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), whole) and np.array_equal(np.concatenate([p[1] for p in parts]), seeds)
+    cfg5 = dict(bench.CONFIGS["c5"]); cfg5["gargs"] = dict(ncirc=3); cfg5["restarts"] = 6
+    forms5, _i, _x = bench.build_problem(cfg5)
+    w5, s5 = bench.starts_for(cfg5, forms5, None, 0, 6, 0, False)
+    p5 = [bench.starts_for(cfg5, forms5, None, *bench.shard(6, r, 4), r, False) for r in range(4)]
+    assert np.array_equal(np.concatenate([p[0] for p in p5]), w5) and np.array_equal(w5[2], np.random.RandomState(2).randn(7))

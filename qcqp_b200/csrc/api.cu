@@ -89,6 +89,15 @@ extern "C" int qcqp_eval(qcqp_pack* pack, const double* X, int32_t R, double* f0
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// device-visible alias of a PINNED host array (cudaHostAlloc / cudaHostRegister / torch pin_memory), or null
+static double* pinned_alias(const void* host)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return (double*)at.devicePointer;
+}
+
 static int check_cd_params(const qcqp_cd_params* p)
 {
     if (!p) return fail(QCQP_ERR_INVALID, "qcqp_cd_improve: null params");
@@ -122,8 +131,12 @@ extern "C" int qcqp_cd_improve(qcqp_pack* pack, const qcqp_cd_params* params, co
     qcqp_cd_stats* dS = ar.take<qcqp_cd_stats>(R * sizeof(qcqp_cd_stats));
     QCQP_CUDA_TRY(cudaMemcpyAsync(dX0, X0, R * n * 8, cudaMemcpyHostToDevice, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(dR, rng, R * sizeof(qcqp_rng_state), cudaMemcpyHostToDevice, 0));
-    TRY(cd_launch(pack, params, dX0, R, dR, dX, dF, dM, dS, 0));
-    QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, R * n * 8, cudaMemcpyDeviceToHost, 0));
+    pack->x_mirror = pinned_alias(X); pack->x_mirror_done = false;
+    const int rc_cd = cd_launch(pack, params, dX0, R, dR, dX, dF, dM, dS, 0);
+    const bool delivered = pack->x_mirror_done;
+    pack->x_mirror = nullptr; pack->x_mirror_done = false;
+    TRY(rc_cd);
+    if (!delivered) QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, R * n * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF, R * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, R * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(rng, dR, R * sizeof(qcqp_rng_state), cudaMemcpyDeviceToHost, 0));
@@ -267,9 +280,13 @@ extern "C" int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* param
     mt_seed_kernel<<<(S + 127) / 128, 128, 0, 0>>>(dSeeds, dR, S);
     QCQP_CUDA_TRY(cudaGetLastError());
     TRY(sdr_launch(pack, pack->sdr_mu, pack->sdr_F, Z ? dZ : nullptr, seed, S, dX0, dFs, dMs, 0));
-    TRY(cd_launch(pack, params, dX0, S, dR, dX, dF0, dM, dS, 0));
+    pack->x_mirror = pinned_alias(X); pack->x_mirror_done = false;
+    const int rc_cd = cd_launch(pack, params, dX0, S, dR, dX, dF0, dM, dS, 0);
+    const bool delivered = pack->x_mirror_done;
+    pack->x_mirror = nullptr; pack->x_mirror_done = false;
+    TRY(rc_cd);
     if (best_idx) TRY(best_launch(dF0, dM, S, 1e-4, dBest, nullptr, nullptr, 0));
-    QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, S * n * 8, cudaMemcpyDeviceToHost, 0));
+    if (!delivered) QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, S * n * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF0, S * 8, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, S * 8, cudaMemcpyDeviceToHost, 0));
     if (X0) QCQP_CUDA_TRY(cudaMemcpyAsync(X0, dX0, S * n * 8, cudaMemcpyDeviceToHost, 0));

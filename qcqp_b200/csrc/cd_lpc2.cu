@@ -83,7 +83,7 @@ struct Lpc2Mem {
 template <int CH, bool PROF>   // CH: 16-byte chunks of g per worker lane (rows of up to 64 CH doubles); PROF: clock64 breakdown
 __global__ void __launch_bounds__(64, 7)
 cd_lpc2_kernel(const __grid_constant__ CUtensorMap tmapD, PackView P, LpcView V, CdK prm, int R, qcqp_rng_state* rngs, double* X,
-               const double* __restrict__ G, qcqp_cd_stats* stats_out, unsigned long long* ctr, unsigned long long* prof_)
+               const double* __restrict__ G, qcqp_cd_stats* stats_out, unsigned long long* ctr, unsigned long long* prof_, double* xmirror)
 {
     unsigned long long* const prof = PROF ? prof_ : nullptr;
     constexpr int CQ = LPC2_CQ;
@@ -451,6 +451,12 @@ cd_lpc2_kernel(const __grid_constant__ CUtensorMap tmapD, PackView P, LpcView V,
     }
     post(LPC2_CMD_FIN, 0.0);
     __syncwarp();
+    // the finished point straight into the caller's pinned result array (when there is one): the read-back of X overlaps the rest
+    // of the launch instead of following it
+    if (xmirror) {
+        double* xm = xmirror + rr * (size_t)n;
+        for (int k = lane; k < n; k += 32) xm[k] = xg[k];
+    }
     if (lane == 0) {
         rngs[rr].pos = pos;
         stats_out[rr] = st;
@@ -521,7 +527,8 @@ static int lpc2_launch_k(qcqp_pack* p, const CdK& k, int R, qcqp_rng_state* drng
     QCQP_CUDA_TRY(cudaFuncSetAttribute(cd_lpc2_kernel<CH, PROF>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUtensorMap tm;
     memcpy(&tm, p->tmap, sizeof(tm));
-    cd_lpc2_kernel<CH, PROF><<<R, 64, smem, stream>>>(tm, p->v, p->lpc, k, R, drng, dX, G, dstats, p->d_ctr, dprof);
+    cd_lpc2_kernel<CH, PROF><<<R, 64, smem, stream>>>(tm, p->v, p->lpc, k, R, drng, dX, G, dstats, p->d_ctr, dprof, p->x_mirror);
+    if (p->x_mirror) p->x_mirror_done = true;
     QCQP_CUDA_TRY(cudaGetLastError());
     return QCQP_OK;
 }

@@ -128,6 +128,11 @@ struct qcqp_pack {
     // device counters of the last qcqp_cd_improve* call (qcqp_cd_get_counters): [0] rows of P_0 applied, [1] diagonal blocks
     // fetched, [2] rows read by from-scratch refreshes, [3] bytes requested from L2, [4..7] reserved
     unsigned long long* d_ctr;
+    // host-buffer entry points: device-visible alias of the caller's PINNED result array X (else null).  A kernel that can deliver
+    // every restart's point itself, as the restart finishes, writes through it and sets x_mirror_done; the read-back of X then
+    // overlaps the tail of the launch instead of following it.
+    double* x_mirror;
+    bool x_mirror_done;
 };
 
 namespace qcqp {

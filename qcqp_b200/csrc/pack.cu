@@ -272,7 +272,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     std::memset(&p->v, 0, sizeof(p->v));
     std::memset(&p->info, 0, sizeof(p->info));
     p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->ws2 = nullptr; p->ws2_bytes = 0; p->has_eig = false; p->lpc_ok = false; p->sdr_mu = nullptr; p->sdr_F = nullptr; p->sdr_ok = false;
-    p->ev_ok = false; p->ev_count = 0; p->tmap_state = 0; p->d_ctr = nullptr;
+    p->ev_ok = false; p->ev_count = 0; p->tmap_state = 0; p->d_ctr = nullptr; p->x_mirror = nullptr; p->x_mirror_done = false;
     std::memset(&p->lpc, 0, sizeof(p->lpc));
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;

@@ -135,6 +135,39 @@ def test_sdr_cd_pipeline_equals_separate_calls():
     pack.close(); pack2.close()
 
 
+def test_pinned_result_array_is_filled_by_the_kernel():
+    """Host-buffer calls whose result array X is PINNED take the in-kernel delivery path of cd_lpc2_kernel (every restart writes its
+    finished point through the mapped alias of X; no trailing device-to-host copy of X): same bytes as the pageable path, for the
+    pipeline and for qcqp_cd_improve, including restarts that never reach phase 2."""
+    import torch
+    from qcqp_b200 import engine, problems as pb
+    n, S = 100, 96                                                           # R >= 64, n > 64: phase 2 runs in cd_lpc2_kernel
+    forms, _ = pb.boolean_least_squares(n, 150, seed=3)
+    pack = engine.Pack(forms)
+    mu, _Sg, F = engine.sdr_factor(pb.synthetic_sdr_solution(n, rank=5, seed=2))
+    Z = np.random.RandomState(8).standard_normal((S, n))
+    seeds = 500 + np.arange(S)
+    ref = pack.sdr_cd_pipeline(seeds, mu=mu, F=F, Z=Z, want_draws=True)
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    out = (pin(S, n), pin(S), pin(S))
+    out[0][:] = np.nan
+    res = pack.sdr_cd_pipeline(seeds, Z=Z, out=out)
+    assert res["X"] is out[0] and np.array_equal(out[0], ref["X"]) and np.array_equal(out[1], ref["f0"]) and np.array_equal(out[2], ref["maxviol"])
+    assert res["best"] == ref["best"]
+    # qcqp_cd_improve with a pinned X: monkey-level check through ctypes (engine.cd_improve allocates pageable arrays)
+    import ctypes as C
+    from qcqp_b200 import _lib
+    L = _lib.load()
+    X0 = np.ascontiguousarray(ref["X0"]); Xp = pin(S, n); Xp[:] = np.nan
+    f0 = np.empty(S); mv = np.empty(S)
+    rng = engine.rng_states(seeds=seeds)
+    prm = _lib.CdParams(1000, 1e-2, 1e-4, 1, 0, 0)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(L.qcqp_cd_improve(pack.handle, C.byref(prm), ptr(X0), S, C.cast(rng, C.c_void_p), ptr(Xp), ptr(f0), ptr(mv), None))
+    assert np.array_equal(Xp, ref["X"]) and np.array_equal(f0, ref["f0"])
+    pack.close()
+
+
 def test_facade_suggest_improve_batch_equals_two_step_flow():
     """QCQP.suggest_improve(samples=S, seed=s) == suggest(SDR, samples=S) followed by improve(COORD_DESCENT, seed=s)."""
     from qcqp_b200 import QCQP, COORD_DESCENT, SDR, problems as pb

@@ -114,7 +114,7 @@ extern "C" int qcqp_probe_fp64_peaks(double* dmma_tflops, double* dfma_tflops)
     QCQP_CUDA_TRY(cudaGetDevice(&dev));
     double* sink = nullptr;
     QCQP_CUDA_TRY(cudaMalloc((void**)&sink, 8));
-    const int grid = num_sms(dev) * 4, iters = 20000;
+    const int grid = num_sms(dev) * 4, iters = 4000;
     cudaEvent_t e0, e1;
     QCQP_CUDA_TRY(cudaEventCreate(&e0)); QCQP_CUDA_TRY(cudaEventCreate(&e1));
     double best_m = 0.0, best_f = 0.0;

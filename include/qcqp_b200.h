@@ -32,7 +32,8 @@ typedef enum {
     QCQP_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
     QCQP_ERR_NOMEM = -3,     /* host or device allocation failed */
     QCQP_ERR_CAPACITY = -4,  /* problem exceeds a shared-memory capacity of the kernels */
-    QCQP_ERR_NO_DEVICE = -5  /* no CUDA device: the engine has no CPU fallback */
+    QCQP_ERR_NO_DEVICE = -5, /* no CUDA device: the engine has no CPU fallback */
+    QCQP_ERR_NCCL = -6       /* NCCL could not be loaded, or an NCCL call failed (multi-GPU best pick) */
 } qcqp_status;
 
 enum { QCQP_RELOP_NONE = 0, QCQP_RELOP_LE = 1, QCQP_RELOP_EQ = 2 };
@@ -215,6 +216,25 @@ int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* params, const do
 int qcqp_best(const double* f0, const double* maxviol, int32_t R, double tol, int32_t* best_idx);
 int qcqp_best_device(const double* df0, const double* dmaxviol, int32_t R, double tol, int32_t* dbest_idx,
                      int64_t* dbest_bucket, double* dbest_f0, void* stream);
+
+/* ---- best pick ACROSS GPUs (QCQPForm.better, utilities.py:135-146, over the restarts of every rank).
+ *      One process per GPU; restarts are sharded contiguously with no collective on the data path; this is the only exchange:
+ *      ONE NCCL all-gather of (f0, maxviol, global index, x) per rank, then the same `better` fold over the ranks.  NCCL is
+ *      bound at run time (dlopen of libnccl.so.2; QCQP_NCCL_LIB overrides the name).
+ *        qcqp_comm_unique_id  rank 0 creates the 128-byte NCCL id; the caller hands it to the other ranks (MPI, a file, a socket).
+ *        qcqp_comm_create     collective over the ranks; binds the communicator to the CUDA device that is current.
+ *        qcqp_best_multi      collective.  df0 / dmaxviol / dX: this rank's R restarts on the device (R may be 0);
+ *                             index_offset: global index of its first restart (ranks own increasing, disjoint ranges, so that
+ *                             "the later index wins an exact tie" holds across ranks as it does inside qcqp_best).
+ *                             Returns, identically on every rank: the winner's global index, its rank, (f0, maxviol), and its
+ *                             point in dx_best (device, [n]; may be NULL).  Synchronises `stream` before returning. ---------- */
+typedef struct qcqp_comm qcqp_comm;
+int qcqp_comm_unique_id(void* id128 /* out: 128 bytes */);
+int qcqp_comm_create(int32_t rank, int32_t nranks, const void* id128, qcqp_comm** out);
+void qcqp_comm_destroy(qcqp_comm* comm);
+int qcqp_best_multi(qcqp_comm* comm, const double* df0 /*[R]*/, const double* dmaxviol /*[R]*/, const double* dX /*[R][n] or NULL*/,
+                    int32_t R, int32_t n, double tol, int64_t index_offset, int64_t* best_index, int32_t* best_rank,
+                    double* best_f0, double* best_maxviol, double* dx_best /*[n] device or NULL*/, void* stream);
 
 /* ---- measurement helpers (no counterpart in the reference): the ceilings bench.py reports its roofline fractions against,
  *      measured on the device that is current, with CUDA events.  The path is FP64 and its matrices are L2-resident, so the

@@ -82,6 +82,12 @@ EXPORTS = {
                                        C.c_void_p, C.c_void_p]),
     "qcqp_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "qcqp_best_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcqp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "qcqp_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "qcqp_comm_destroy": (None, [C.c_void_p]),
+    "qcqp_best_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int64,
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p,
+                                  C.c_void_p]),
     "qcqp_probe_l2_bandwidth": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
     "qcqp_probe_fp64_peaks": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

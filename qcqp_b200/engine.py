@@ -219,6 +219,44 @@ class Pack:
         return res
 
 
+class Comm:
+    """NCCL communicator owned by the library (qcqp_comm_*): the best pick across GPUs without torch.distributed on the data
+    path.  Rank 0 calls Comm.unique_id() and hands the 128 bytes to the other ranks; every rank then builds Comm(rank, n, id)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        check(_lib.load().qcqp_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def __init__(self, rank, nranks, unique_id):
+        if len(unique_id) != 128:
+            raise Exception("the NCCL unique id is 128 bytes")
+        h = C.c_void_p()
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        check(_lib.load().qcqp_comm_create(int(rank), int(nranks), C.cast(buf, C.c_void_p), C.byref(h)))
+        self._h, self.rank, self.nranks = h, int(rank), int(nranks)
+
+    def best(self, d_f0, d_maxviol, d_X, R, n, index_offset=0, d_xbest=0, tol=1e-4, stream=0):
+        """Device pointers (ints) of this rank's f0[R], maxviol[R], X[R][n]; returns (global index, rank, f0, maxviol) of the best
+        restart over all ranks in QCQPForm.better order; its point is written to d_xbest (device pointer, may be 0)."""
+        bi, br, bf, bv = C.c_int64(-1), C.c_int32(-1), C.c_double(0), C.c_double(0)
+        check(_lib.load().qcqp_best_multi(self._h, d_f0, d_maxviol, d_X, int(R), int(n), float(tol), int(index_offset), C.byref(bi), C.byref(br),
+                                          C.byref(bf), C.byref(bv), d_xbest, stream))
+        return int(bi.value), int(br.value), float(bf.value), float(bv.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().qcqp_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def best(f0, maxviol, tol=1e-4):
     """Index of the best point in QCQPForm.better order (utilities.py:135-146)."""
     f0 = np.ascontiguousarray(f0, dtype=np.float64).ravel(); mv = np.ascontiguousarray(maxviol, dtype=np.float64).ravel()

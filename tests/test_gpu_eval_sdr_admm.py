@@ -145,3 +145,26 @@ def test_best_pick_order():
             f0[rs.randint(0, R)] = np.nan
         want = local_best(f0, mv)[2]
         assert engine.best(f0, mv) == want
+
+
+def test_best_multi_single_rank_equals_best():
+    """qcqp_best_multi on a one-rank communicator (the GPU box of the test tier has one device; tools/multi_probe.py is the
+    two-rank run): same pick as qcqp_best, the winner's point and values returned, an empty shard and NaN objectives handled."""
+    import torch
+    from qcqp_b200 import engine
+    from qcqp_b200.dist import local_best
+    dev = torch.device("cuda:0")
+    comm = engine.Comm(0, 1, engine.Comm.unique_id())
+    rs = np.random.RandomState(3)
+    for R, n in ((1, 4), (50, 7), (1000, 33)):
+        f0 = np.round(rs.randn(R), 1); mv = np.abs(rs.randn(R)) * 2e-4; X = rs.randn(R, n)
+        if R > 10:
+            f0[3] = np.nan
+        df, dv, dX = (torch.from_numpy(a).to(dev) for a in (f0, mv, X))
+        dx = torch.zeros(n, dtype=torch.float64, device=dev)
+        gi, rk, bf, bv = comm.best(df.data_ptr(), dv.data_ptr(), dX.data_ptr(), R, n, index_offset=100, d_xbest=dx.data_ptr())
+        b = local_best(f0, mv)[2]
+        assert (gi, rk) == (100 + b, 0) and bf == f0[b] and bv == mv[b] and np.array_equal(dx.cpu().numpy(), X[b])
+    gi, rk, bf, bv = comm.best(0, 0, 0, 0, 5)              # nothing to offer
+    assert gi == -1 and rk == -1 and np.isinf(bf)
+    comm.close()

@@ -13,7 +13,8 @@
  *   - all floating point is IEEE binary64; matrices are row-major; index arrays are int32 unless noted.
  *   - "host" entry points take caller-owned host buffers and return after the stream is synchronised.
  *     "_device" entry points take device pointers (cudaMalloc'ed / torch tensors' data_ptr()) and a
- *     cudaStream_t passed as void*; they only enqueue work.
+ *     cudaStream_t passed as void*; they only enqueue work -- after qcqp_pack_reserve, or once the pack's
+ *     grow-on-demand workspaces have reached the batch size (the first call at a new size allocates).
  *   - a pack is bound to the CUDA device that was current when it was created; it is not thread-safe
  *     (neither is the reference: it caches state on prob/f, utilities.py:46,129-130).
  */
@@ -145,6 +146,11 @@ const char* qcqp_version(void);
 int qcqp_pack_create(const qcqp_pack_desc* desc, qcqp_pack** out);
 void qcqp_pack_destroy(qcqp_pack* pack);
 int qcqp_pack_get_info(const qcqp_pack* pack, qcqp_pack_info* info);
+/* Sizes every grow-on-demand device buffer of the pack for batches of up to R restarts / draws (and K rho values), so that the
+ * `_device` calls that follow only enqueue work: no cudaMalloc / cudaFree (an implicit device-wide synchronisation, illegal during
+ * CUDA-graph capture) inside a stream of work.  Without it the first call at a new size grows the buffers.  A pack is
+ * single-stream: its workspaces are shared by its calls (the reference's seam is not re-entrant either). */
+int qcqp_pack_reserve(qcqp_pack* pack, int32_t R, int32_t K);
 
 /* ---- batched evaluation: QuadraticFunction.eval / QCQPForm.violations for R points
  *      (utilities.py:49-50, 56-62, 133-134; the (f0, max violation) pair of qcqp.py:399-401, 415-417) ---------- */

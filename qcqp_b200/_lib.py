@@ -60,6 +60,7 @@ EXPORTS = {
     "qcqp_pack_create": (C.c_int, [C.POINTER(PackDesc), C.POINTER(C.c_void_p)]),
     "qcqp_pack_destroy": (None, [C.c_void_p]),
     "qcqp_pack_get_info": (C.c_int, [C.c_void_p, C.POINTER(PackInfo)]),
+    "qcqp_pack_reserve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "qcqp_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qcqp_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qcqp_cd_improve": (C.c_int, [C.c_void_p, C.POINTER(CdParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

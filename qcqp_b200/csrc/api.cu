@@ -163,6 +163,35 @@ extern "C" int qcqp_cd_get_timing(qcqp_pack* pack, double* ms, int32_t* count)
     return QCQP_OK;
 }
 
+// Sizes every grow-on-demand device buffer of the pack for batches of up to R restarts / draws (and K rho values), so that the
+// `_device` entry points that follow never allocate: no implicit device-wide synchronisation from cudaFree / cudaMalloc inside a
+// stream of work, and they become legal inside CUDA-graph capture.  (A pack stays single-stream: its workspaces are shared.)
+extern "C" int qcqp_pack_reserve(qcqp_pack* pack, int32_t R, int32_t K)
+{
+    TRY(check_pack(pack, "qcqp_pack_reserve"));
+    if (R < 0 || K < 0) return fail(QCQP_ERR_INVALID, "qcqp_pack_reserve: negative size");
+    const size_t n = pack->v.n, m = pack->v.m, Rz = (size_t)R, Kz = (size_t)(K > 0 ? K : 1);
+    const size_t npad = (n + 1) & ~(size_t)1;
+    // coordinate descent: G = X P0 + stats (separable dense path); cached f_j + coefficient scratch (general / CTA-per-restart)
+    size_t ws = Rz * npad * 8 + 256 + Rz * sizeof(qcqp_cd_stats);
+    const size_t gen = Rz * (m + 1) * 8 + 512 + (pack->v.max_inc > 1024 ? Rz * (size_t)pack->v.max_inc * 28 : 0);
+    if (gen > ws) ws = gen;
+    // ADMM (run-per-CTA kernel): xs / us per run
+    const size_t adm = Kz * Rz * 2 * m * n * 8 + 4096;
+    if (pack->has_eig && adm > ws) ws = adm;
+    TRY(ensure_workspace(pack, ws));
+    // batched eval / SDR: row-dot partials of the dense forms and device-generated normals
+    TRY(ensure_workspace2(pack, Rz * (size_t)(pack->v.n_dense + 1) * ((n + 63) / 64 + 1) * 8 + Rz * n * 8 + 4096));
+    // host-buffer entry points: staging arena of the largest call (the SDR -> CD pipeline)
+    TRY(ensure_io(pack, 3 * Arena::pad(Rz * n * 8) + 4 * Arena::pad(Rz * 8) + Arena::pad(Rz * sizeof(qcqp_rng_state)) +
+                            Arena::pad(Rz * sizeof(qcqp_cd_stats)) + Arena::pad(Rz * 4) + Arena::pad(64) + Arena::pad(n * n * 8) + Arena::pad(n * 8)));
+    if (pack->objective_dense && !pack->sdr_mu) {
+        QCQP_CUDA_TRY(cudaMalloc((void**)&pack->sdr_mu, n * 8));
+        QCQP_CUDA_TRY(cudaMalloc((void**)&pack->sdr_F, n * n * 8));
+    }
+    return QCQP_OK;
+}
+
 // Device counters of the last qcqp_cd_improve* call on this pack (zeroed at its start; kernels that do not count leave zeros):
 // out[0] rows of P_0 applied to g (accepted phase-2 moves), out[1] 32 x 32 diagonal blocks fetched, out[2] rows read by
 // from-scratch refreshes of g, out[3] bytes requested from L2 by the phase-2 kernel.  Call after synchronising the stream.

@@ -682,7 +682,7 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     if (v.n_dense > 0) return fail(QCQP_ERR_INVALID, "qcqp_cd_improve: the CTA-per-restart kernel handles sparse forms only");
     const int sms = num_sms(p->device);
     int T = (R <= sms) ? 512 : (R <= 2 * sms ? 256 : 128);
-    if (force_threads == 128 || force_threads == 256 || force_threads == 512) T = force_threads;
+    if (force_threads == 64 || force_threads == 128 || force_threads == 256 || force_threads == 512) T = force_threads;
     const int NW = T / 32;
     BlkLayout l;
     memset(&l, 0, sizeof(l));
@@ -726,6 +726,7 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     // more restarts than 4 CTAs per SM can hold: the 64-register build of the 128-thread kernel, 8 CTAs per SM
     const char* f8 = getenv("QCQP_BLK_CTAS");
     const bool dense8 = (T == 128) && (f8 ? atoi(f8) == 8 : R > 4 * sms);
+    if (T == 64) return blk_launch_t<64, 12>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (dense8) return blk_launch_t<128, 8>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (T == 512) return blk_launch_t<512, 1>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (T == 256) return blk_launch_t<256, 2>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);

@@ -85,10 +85,13 @@ __device__ __forceinline__ void scan_hole_chunk(double* clo, double* chi, const 
     hs.havePrev = true;
 }
 
-// order-preserving map double -> uint64 (never fed NaN: the fold's L and H only ever take values that won a comparison)
+// order-preserving map double -> uint64 (never fed NaN: the fold's L and H only ever take values that won a comparison).
+// -0.0 is mapped onto +0.0 first: the reference's sweep keys its events in a dict, where 0.0 and -0.0 are ONE key (and the
+// lane-by-lane Fold::merge compares with ==), so two right ends +0.0 and -0.0 in different lanes must share a key here too --
+// otherwise their multiplicities would not add up and a piece ending at 0 that the reference hides would be reported.
 __device__ __forceinline__ unsigned long long dkey(double v)
 {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 __device__ __forceinline__ double dunkey(unsigned long long k)
@@ -114,7 +117,7 @@ __device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k)
 
 // all-reduce of the per-lane folds.  Same result as merging lane by lane (Fold::merge): L = max, H = min, mu = the
 // multiplicities of the lanes that hold H (lanes that folded nothing carry H = +inf with mu = 0), counts add up.
-// (-0.0 and +0.0 compare equal in the lane-by-lane merge and are ordered here; nothing downstream tells them apart.)
+// (-0.0 and +0.0 compare equal in the lane-by-lane merge; dkey maps both to one key.)
 __device__ __forceinline__ void fold_allreduce(Fold& f)
 {
     const unsigned long long kh = dkey(f.H);

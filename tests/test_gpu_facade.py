@@ -168,6 +168,53 @@ def test_pinned_result_array_is_filled_by_the_kernel():
     pack.close()
 
 
+def test_reserved_pack_runs_under_cuda_graph_capture():
+    """After qcqp_pack_reserve the `_device` entry points only enqueue work: the whole step (SDR draws -> coordinate descent ->
+    best pick) is captured into a CUDA graph on a side stream and replayed; same bytes as the eager calls."""
+    import ctypes as C
+    import torch
+    from qcqp_b200 import _lib, engine, problems as pb
+    L = _lib.load()
+    dev = torch.device("cuda:0")
+    n, R = 100, 128
+    forms, _ = pb.boolean_least_squares(n, 150, seed=3)
+    pack = engine.Pack(forms)
+    _lib.check(L.qcqp_pack_reserve(pack.handle, R, 1))
+    mu, _Sg, F = engine.sdr_factor(pb.synthetic_sdr_solution(n, rank=5, seed=2))
+    Z = np.random.RandomState(8).standard_normal((R, n))
+    rng_host = engine.rng_states(seeds=300 + np.arange(R))
+    d_mu, d_F, d_Z = (torch.from_numpy(a).to(dev) for a in (mu, F, Z))
+    d_rng0 = torch.from_numpy(engine.rng_states_as_tensor_bytes(rng_host)).to(dev); d_rng = torch.empty_like(d_rng0)
+    d_X0 = torch.empty((R, n), dtype=torch.float64, device=dev); d_X = torch.empty_like(d_X0)
+    d_f = torch.empty(R, dtype=torch.float64, device=dev); d_v = torch.empty_like(d_f); d_fs = torch.empty_like(d_f); d_vs = torch.empty_like(d_f)
+    d_st = torch.zeros(R * C.sizeof(_lib.CdStats), dtype=torch.uint8, device=dev)
+    d_best = torch.zeros(1, dtype=torch.int32, device=dev)
+    prm = _lib.CdParams(1000, 1e-2, 1e-4, 1, 0, 0)
+
+    def step(stream):
+        d_rng.copy_(d_rng0)
+        _lib.check(L.qcqp_sdr_sample_eval_device(pack.handle, d_mu.data_ptr(), d_F.data_ptr(), d_Z.data_ptr(), 0, R, d_X0.data_ptr(), d_fs.data_ptr(),
+                                                  d_vs.data_ptr(), stream))
+        _lib.check(L.qcqp_cd_improve_device(pack.handle, C.byref(prm), d_X0.data_ptr(), R, d_rng.data_ptr(), d_X.data_ptr(), d_f.data_ptr(), d_v.data_ptr(),
+                                             d_st.data_ptr(), stream))
+        _lib.check(L.qcqp_best_device(d_f.data_ptr(), d_v.data_ptr(), R, 1e-4, d_best.data_ptr(), None, None, stream))
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        step(side.cuda_stream)                                   # eager, warms every lazily created object (events, tensor map)
+    side.synchronize()
+    want = (d_X.clone(), d_f.clone(), d_v.clone(), int(d_best.item()))
+    d_X.zero_(); d_f.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        step(side.cuda_stream)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(d_X, want[0]) and torch.equal(d_f, want[1]) and torch.equal(d_v, want[2]) and int(d_best.item()) == want[3]
+    pack.close()
+
+
 def test_facade_suggest_improve_batch_equals_two_step_flow():
     """QCQP.suggest_improve(samples=S, seed=s) == suggest(SDR, samples=S) followed by improve(COORD_DESCENT, seed=s)."""
     from qcqp_b200 import QCQP, COORD_DESCENT, SDR, problems as pb

@@ -173,7 +173,7 @@ extern "C" int qcqp_pack_reserve(qcqp_pack* pack, int32_t R, int32_t K)
     const size_t n = pack->v.n, m = pack->v.m, Rz = (size_t)R, Kz = (size_t)(K > 0 ? K : 1);
     const size_t npad = (n + 1) & ~(size_t)1;
     // coordinate descent: G = X P0 + stats (separable dense path); cached f_j + coefficient scratch (general / CTA-per-restart)
-    size_t ws = Rz * npad * 8 + 256 + Rz * sizeof(qcqp_cd_stats);
+    size_t ws = Rz * npad * 8 + 512 + Rz * sizeof(qcqp_cd_stats) + Rz * n * 40;
     const size_t gen = Rz * (m + 1) * 8 + 512 + (pack->v.max_inc > 1024 ? Rz * (size_t)pack->v.max_inc * 28 : 0);
     if (gen > ws) ws = gen;
     // ADMM (run-per-CTA kernel): xs / us per run

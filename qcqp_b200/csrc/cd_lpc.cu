@@ -222,13 +222,55 @@ __device__ __forceinline__ void lpc_axpy_multi(const PackView& P, const LpcMem& 
     __syncwarp();
 }
 
+// Draw-free bisection of ONE coordinate of phase 1 (qcqp.py:113-131), computed ahead of the sweep by lpc_p1_pre_kernel: whether a
+// bisection probe is feasible depends on x_k alone (separable constraints, no objective in phase 1), and in the FIRST sweep x_k is
+// still the start value when its step comes, so the whole sweep's bisections are independent of each other: one thread per
+// (restart, coordinate) at full occupancy instead of one warp per restart walking them 32 at a time.
+struct LpcPre {
+    double l0, h0, l1, h1;   // pieces of the last feasible probe
+    int words;               // MT19937 words the reference consumes on this coordinate
+    int flags;               // lastn | moved << 4 | hard << 5
+};
+
+__global__ void __launch_bounds__(256) lpc_p1_pre_kernel(PackView P, LpcView V, CdK prm, const double* __restrict__ X0, int R, LpcPre* __restrict__ pre)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = P.n;
+    if (idx >= (size_t)R * n) return;
+    const int k = (int)(idx % n);
+    const double p = V.c_p[k], q = V.c_q[k], r = V.c_r[k], xk = X0[idx];
+    const int rel = V.c_rel[k];
+    const double tol = prm.tol, viol_tol = prm.viol_tol;
+    const double viol = violation_of(rel, onevar_eval(p, q, r, xk));
+    double ss = -tol, es = viol - viol_tol;
+    LpcPre e;
+    e.l0 = e.h0 = e.l1 = e.h1 = 0.0; e.words = 0;
+    int lastn = 0;
+    bool moved = false, hard = false;
+    while (es - ss > tol) {
+        const double s = (ss + es) / 2;
+        double a0, b0, a1, b1;
+        const int nC = single_constraint_pieces(p, q, r, rel, s, &a0, &b0, &a1, &b1);
+        if (nC > 0) {
+            e.words += (nC == 2) ? 3 : 2;
+            lastn = nC; e.l0 = a0; e.h0 = b0; e.l1 = a1; e.h1 = b1;
+            moved = true;
+            es = s;
+            if (is_inf(a0) || is_inf(b0) || (nC == 2 && (is_inf(a1) || is_inf(b1))) || nC > 2) hard = true;
+        } else ss = s;
+    }
+    e.flags = (lastn & 15) | (moved ? 16 : 0) | (hard ? 32 : 0);
+    pre[idx] = e;
+}
+
 // stage 0: the whole of improve_coord_descent in one launch.
 // stage 1: phase 1 only (x, stream and stats are written back).   stage 2: phase 2 only, starting from stage 1's output with
 // g = P_0 x supplied in G (one tiled GEMM for all restarts instead of one latency-bound GEMV per warp); the returned
 // (f0, maxviol) then come from the batched eval kernels.
 __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, CdK prm, int stage, const double* __restrict__ X0, int R,
                                                      qcqp_rng_state* rngs, double* X, const double* __restrict__ G,
-                                                     double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out)
+                                                     double* __restrict__ f0_out, double* __restrict__ mv_out, qcqp_cd_stats* stats_out,
+                                                     const LpcPre* __restrict__ pre)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x;
@@ -283,7 +325,14 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                 int words = 0, lastn = 0;
                 double l0 = 0.0, h0 = 0.0, l1 = 0.0, h1 = 0.0;
                 bool moved = false, hard = false;
-                if (act) {
+                if (pre && t == 0) {
+                    // first sweep: the bisections were computed ahead, one thread per coordinate (lpc_p1_pre_kernel)
+                    if (act) {
+                        const LpcPre e = pre[rr * n + k];
+                        words = e.words; lastn = e.flags & 15; moved = (e.flags & 16) != 0; hard = (e.flags & 32) != 0;
+                        l0 = e.l0; h0 = e.h0; l1 = e.l1; h1 = e.h1;
+                    }
+                } else if (act) {
                     while (es - ss > tol) {
                         const double s = (ss + es) / 2;
                         double a0, b0, a1, b1;
@@ -659,17 +708,26 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     if (p->lpc.obj_dense && R >= 64) {
         // phase 1 -> G = X P_0 (tiled GEMM) -> phase 2 -> batched (f0, maxviol)
         const size_t gbytes = ((size_t)R * npad * 8 + 255) & ~(size_t)255;
-        int rc = ensure_workspace(p, gbytes + (size_t)R * sizeof(qcqp_cd_stats));
+        const size_t sbytes = ((size_t)R * sizeof(qcqp_cd_stats) + 255) & ~(size_t)255;
+        const char* ep = getenv("QCQP_LPC_PRE");                      // QCQP_LPC_PRE=0: bisect inside the sweep kernel (A/B; same results)
+        const bool use_pre = k.phase1 && !(ep && ep[0] == '0');
+        int rc = ensure_workspace(p, gbytes + sbytes + (use_pre ? (size_t)R * n * sizeof(LpcPre) : 0));
         if (rc != QCQP_OK) return rc;
         double* G = (double*)p->ws;
         qcqp_cd_stats* stats = dstats ? dstats : (qcqp_cd_stats*)((char*)p->ws + gbytes);
+        LpcPre* pre = use_pre ? (LpcPre*)((char*)p->ws + gbytes + sbytes) : nullptr;
         if (!p->ev_ok) {
             for (int i = 0; i < 6; i++) QCQP_CUDA_TRY(cudaEventCreate(&p->ev[i]));
             p->ev_ok = true;
         }
         p->ev_count = 0;
         QCQP_CUDA_TRY(cudaEventRecord(p->ev[0], stream));
-        cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 1, dX0, R, drng, dX, nullptr, df0, dmv, stats);
+        if (pre) {
+            const size_t tot = (size_t)R * n;
+            lpc_p1_pre_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(p->v, p->lpc, k, dX0, R, pre);
+            QCQP_CUDA_TRY(cudaGetLastError());
+        }
+        cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 1, dX0, R, drng, dX, nullptr, df0, dmv, stats, pre);
         QCQP_CUDA_TRY(cudaGetLastError());
         QCQP_CUDA_TRY(cudaEventRecord(p->ev[1], stream));
         rc = gemm_plain_launch(R, n, n, dX, n, p->v.dense_P, p->v.ld, G, npad, stream);
@@ -682,7 +740,7 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
             rc = lpc2_launch(p, k, R, drng, dX, G, stats, stream);
             if (rc != QCQP_OK) return rc;
         } else {
-            cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 2, dX0, R, drng, dX, G, df0, dmv, stats);
+            cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 2, dX0, R, drng, dX, G, df0, dmv, stats, nullptr);
             QCQP_CUDA_TRY(cudaGetLastError());
         }
         QCQP_CUDA_TRY(cudaEventRecord(p->ev[3], stream));
@@ -692,7 +750,7 @@ int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
         p->ev_count = 5;
         return QCQP_OK;
     }
-    cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 0, dX0, R, drng, dX, nullptr, df0, dmv, dstats);
+    cd_lpc_kernel<<<R, 32, smem, stream>>>(p->v, p->lpc, k, 0, dX0, R, drng, dX, nullptr, df0, dmv, dstats, nullptr);
     QCQP_CUDA_TRY(cudaGetLastError());
     return QCQP_OK;
 }

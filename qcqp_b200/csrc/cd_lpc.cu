@@ -597,27 +597,64 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
                 if (done) break;
                 if (moved) lpc_axpy_multi(P, w, k0, moved, mydelta, lane);
             }
+            // sparse objective: the per-coordinate constants of the NEXT aligned window are loaded while this one is decided (they come
+            // from L2; in the late sweeps of a long run nearly every window is quiet and the round trip would be all it costs)
+            double pf_p = 0.0, pf_q = 0.0, pf_r = 0.0, pf_od = 0.0, pf_oq = 0.0;
+            int pf_rel = 0, pf_inc = 0, pf_k0 = -1;
             for (int k0 = 0; !V.obj_dense && k0 < n && !done;) {
                 const int B = (n - k0 < 32) ? (n - k0) : 32;
                 const bool act = lane < B;
                 const int k = k0 + lane;
                 double xk = 0.0, p0 = 0.0, q0 = 0.0, r0 = f0val, xi = 0.0;
                 int rc = 0;
+                double c_p = 0.0, c_q = 0.0, c_r = 0.0, c_od = 0.0, c_oq = 0.0;
+                int c_rel = 0, c_inc = 0;
+                if (pf_k0 == k0) { c_p = pf_p; c_q = pf_q; c_r = pf_r; c_rel = pf_rel; c_od = pf_od; c_oq = pf_oq; c_inc = pf_inc; }
+                else if (act) { c_p = V.c_p[k]; c_q = V.c_q[k]; c_r = V.c_r[k]; c_rel = V.c_rel[k]; c_od = V.o_diag[k]; c_oq = V.o_q[k]; c_inc = V.o_inc[k]; }
+                {
+                    pf_k0 = (k0 + 32 < n) ? k0 + 32 : 0;
+                    const int kp = pf_k0 + lane;
+                    if (kp < n) { pf_p = V.c_p[kp]; pf_q = V.c_q[kp]; pf_r = V.c_r[kp]; pf_rel = V.c_rel[kp]; pf_od = V.o_diag[kp]; pf_oq = V.o_q[kp]; pf_inc = V.o_inc[kp]; }
+                }
+                bool certq = false;      // this step certainly changes nothing
+                const bool use_filter = !(prm.mode & 0x100);
                 if (act) {
-                    const double p = V.c_p[k], q = V.c_q[k], r = V.c_r[k];
-                    const int rel = V.c_rel[k];
+                    const double p = c_p, q = c_q, r = c_r;
+                    const int rel = c_rel;
                     xk = w.x[k];
                     if (!(mrel == rel && mp == p && mq == q && mr == r)) {
                         mnC = single_constraint_pieces(p, q, r, rel, viol_p2, &ml0, &mh0, &ml1, &mh1);
                         mfin = mnC > 0 && mnC <= 2 && !is_inf(ml0) && !is_inf(mh0) && (mnC < 2 || (!is_inf(ml1) && !is_inf(mh1)));
                         mp = p; mq = q; mr = r; mrel = rel;
                     }
-                    if (V.o_inc[k]) {
+                    if (c_inc) {
                         // obj = f0.get_onevar_func(x, k): t2 = P0[k,k], t1 = 2 (P0 z)_k + q0[k], t0 = f0(x) - x_k (t2 x_k + t1)
-                        p0 = V.o_diag[k];
-                        q0 = 2 * (w.g[k] - p0 * xk) + V.o_q[k];
+                        p0 = c_od;
+                        q0 = 2 * (w.g[k] - p0 * xk) + c_oq;
                         r0 = f0val - xk * (p0 * xk + q0);
+                        if (use_filter && mfin && p0 == 0.0) {
+                            // linear restriction (MAXCUT: P_0 has a zero diagonal): the reference compares e q0 + r0 over the endpoints
+                            // e of the pieces, so the minimiser is the smallest endpoint for q0 > 0 and the largest for q0 < 0 -- certain
+                            // as soon as |q0| times the smallest gap between endpoints stands clear (relative 1e-9; rounding is 1e-16) of
+                            // the magnitudes being added.  Exact zeros and near-ties are NOT certain and take the reference arithmetic.
+                            const bool two = (mnC == 2);
+                            const double aq = fabs(q0);
+                            const double emax = two ? mh1 : mh0;
+                            const double gap = two ? fmin(fmin(mh0 - ml0, ml1 - mh0), mh1 - ml1) : (mh0 - ml0);
+                            const double est = (q0 > 0.0) ? ml0 : emax;
+                            certq = gap > 0.0 && aq * gap > 1e-9 * (fabs(f0val) + aq * fmax(fabs(ml0), fabs(emax))) && fabs(est - xk) <= tol;
+                        }
                     }
+                }
+                if (!__ballot_sync(FULL, act && !certq)) {
+                    // a quiet window: update_counter += 1 per step (qcqp.py:172-176)
+                    if (n - uc <= B) { st.steps_p2 += (n - uc); done = true; break; }
+                    uc += B;
+                    st.steps_p2 += B;
+                    k0 += B;
+                    continue;
+                }
+                if (act) {
                     rc = mfin ? choose_point_det_t<true>(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi) : choose_point_det(p0, q0, r0, ml0, mh0, ml1, mh1, mnC, &xi);
                 }
                 const bool wants_move = act && rc == 1 && fabs(xi - xk) > tol;
@@ -687,9 +724,14 @@ __global__ void __launch_bounds__(32, 7) cd_lpc_kernel(PackView P, LpcView V, Cd
 int eval_launch(qcqp_pack* p, const double* dX, int R, double* df0, double* dmv, double* dviol, cudaStream_t stream);
 int gemm_plain_launch(int M, int N, int K, const double* dA, int lda, const double* dB, int ldb, double* dC, int ldc, cudaStream_t stream);
 
-int lpc_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0, double* dmv,
+int lpc_launch(qcqp_pack* p, const CdK& k_in, const double* dX0, int R, qcqp_rng_state* drng, double* dX, double* df0, double* dmv,
                qcqp_cd_stats* dstats, cudaStream_t stream)
 {
+    CdK k = k_in;
+    {
+        const char* eq = getenv("QCQP_LPC_QUIET");     // QCQP_LPC_QUIET=0: no certified quiet-window filter in the sparse loop (A/B; same results)
+        if (eq && eq[0] == '0') k.mode |= 0x100;
+    }
     const int n = p->v.n;
     const int npad = (n + 1) & ~1;
     size_t smem = (size_t)2 * npad * 8 + 624 * 4 + (p->lpc.obj_dense ? 32 * 32 * 8 : 0);

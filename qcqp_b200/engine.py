@@ -146,20 +146,46 @@ class Pack:
             qhat[i] = Q[i].T.dot(qa)
         self.set_eig(lmb, Q, qhat)
 
+    def compute_eig_device(self):
+        """SURVEY 8(f) f-3, opt-in: the m eigendecompositions of utilities.py:160-162 as ONE batched `eigh` on the GPU (torch ->
+        cuSOLVER; a library call, setup code outside every timed region) instead of m LAPACK calls on the host.  (lambda, Q) then
+        differ from LAPACK's in the last bits and in the basis of degenerate eigenspaces (the n - 2 noise eigenvalues of a rank-2
+        constraint): onecons_qcqp's bracket depends on them (SURVEY a-11), so results agree with the host path to ~1e-9, not bit
+        for bit -- tests/test_gpu_eval_sdr_admm.py holds the C4-shaped problem to 1e-6 on (f0, maxviol).  The default stays host."""
+        import torch
+        n, m = self.n, self.m
+        Ps = np.stack([np.asarray(((sp.csr_matrix(f[0]) + sp.csr_matrix(f[0]).T) / 2.).todense()) for f in self.forms[1:]])
+        qs = np.stack([np.asarray(f[1].todense() if sp.issparse(f[1]) else f[1], dtype=np.float64).ravel() for f in self.forms[1:]])
+        dP = torch.from_numpy(Ps).cuda()
+        lmb, Q = torch.linalg.eigh(dP)                                    # [m][n], [m][n][n]
+        qhat = torch.bmm(Q.transpose(1, 2), torch.from_numpy(qs).cuda().unsqueeze(2)).squeeze(2)
+        self.set_eig(lmb.cpu().numpy(), Q.cpu().numpy(), qhat.cpu().numpy())
+
+    def zinv_device(self, rhos):
+        """inverse of 2 (P0 + rho m I) for every rho as one batched Cholesky solve on the GPU (f-3, opt-in; the reference hands
+        the matrix to SuperLU, qcqp.py:224-227)."""
+        import torch
+        P0 = torch.from_numpy(np.asarray(sp.csr_matrix(self.forms[0][0]).todense())).cuda()
+        eye = torch.eye(self.n, dtype=torch.float64, device=P0.device)
+        A = torch.stack([2 * (P0 + float(r) * self.m * eye) for r in np.atleast_1d(rhos)])
+        Lc = torch.linalg.cholesky(A)
+        return np.ascontiguousarray(torch.cholesky_inverse(Lc).cpu().numpy())
+
     def zinv(self, rho):
         """inverse of 2 (P0 + rho m I): the matrix qcqp.py:226-227 factorises for the z-update."""
         P0 = np.asarray(sp.csr_matrix(self.forms[0][0]).todense())
         return np.ascontiguousarray(np.linalg.inv(2 * (P0 + rho * self.m * np.eye(self.n))))
 
-    def admm_improve(self, X0, rhos, num_iters=1000, viol_lim=1e4, tol=1e-2, phase1=True):
-        """improve_admm for every (rho, start) pair (qcqp.py:254-285). Returns (X[K][R][n], f0[K][R], maxviol[K][R], stats)."""
+    def admm_improve(self, X0, rhos, num_iters=1000, viol_lim=1e4, tol=1e-2, phase1=True, setup="host"):
+        """improve_admm for every (rho, start) pair (qcqp.py:254-285). Returns (X[K][R][n], f0[K][R], maxviol[K][R], stats).
+        setup="device": the eigendecompositions and the per-rho inverses are computed on the GPU (f-3, see compute_eig_device)."""
         if not self._has_eig:
-            self.compute_eig()
+            self.compute_eig_device() if setup == "device" else self.compute_eig()
         X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, self.n)
         R = X0.shape[0]
         rhos = np.ascontiguousarray(np.atleast_1d(rhos), dtype=np.float64)
         K = len(rhos)
-        Zinv = np.ascontiguousarray(np.stack([self.zinv(r) for r in rhos]))
+        Zinv = self.zinv_device(rhos) if setup == "device" else np.ascontiguousarray(np.stack([self.zinv(r) for r in rhos]))
         X = np.empty((K, R, self.n)); f0 = np.empty((K, R)); mv = np.empty((K, R))
         stats = (AdmmStats * (K * R))()
         prm = AdmmParams(int(num_iters), float(viol_lim), float(tol), int(bool(phase1)))

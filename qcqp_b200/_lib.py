@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqcqp_b200.so")
+LIB_PATH = os.environ.get("QCQP_B200_LIB") or os.path.join(_HERE, "libqcqp_b200.so")   # override: an instrumented build (tools/blk_prof.py)
 
 RELOP_NONE, RELOP_LE, RELOP_EQ = 0, 1, 2
 RELOP_CODE = {None: RELOP_NONE, "<=": RELOP_LE, "==": RELOP_EQ}

@@ -38,16 +38,6 @@ struct CdLayout {
 
 
 
-struct WarpMem {
-    double* x;
-    double* fval;
-    uint32_t* mt;
-    double2* hx;      // holes (a, b) of the two-interval constraints of this step
-    double* clo; double* chi;
-    double* dd;       // dots of the dense rows of this step, by dense slot
-    double* g;        // gradient mode: g[d][npad] = P_d x for every dense slot
-    int* misc;
-};
 
 enum { PH_P1 = 0, PH_P2 = 1, PH_DONE = 2 };
 
@@ -85,115 +75,6 @@ __device__ __forceinline__ double dense_row_dot_seq(const double* row, const dou
         if (v != 0.0 && c != k) s = s + v * x[c];
     }
     return s;
-}
-
-// tail of onevar_qcqp: f = the all-reduced fold (singles + hulls), nh holes -- in (ra, rb), one per lane, when
-// in_regs, else in w.hx[0..nh).  Lane 0 owns the RNG.  Returns found (warp-uniform); xout/err valid in every lane.
-__device__ __forceinline__ int holes_finish(const WarpMem& w, const Fold& f, int nh, bool in_regs, double ra, double rb, double p0, double q0,
-                                            double r0, MtRng& rng, int lane, double* xout, int* err)
-{
-    *xout = 0.0;
-    *err = 0;
-    int nC = 0;
-    if (f.mcnt == 0) {
-        if (lane == 0) { w.clo[0] = -QCQP_INF; w.chi[0] = QCQP_INF; }   // only the sentinel pair: all of R
-        nC = 1;
-    } else {
-        if (f.nempty > 0 || !(f.L < f.H)) return 0;   // the running total never gets full
-        HoleScan hs;
-        hs.carryM = f.L; hs.prevA = 0.0; hs.havePrev = false; hs.blocked = false; hs.stH = -QCQP_INF; hs.nC = 0;
-        if (nh > 0) {
-            if (in_regs || nh <= 32) {
-                double a = ra, b = rb;
-                if (!in_regs) {
-                    a = QCQP_INF; b = QCQP_INF;
-                    if (lane < nh) { const double2 t = w.hx[lane]; a = t.x; b = t.y; }
-                }
-                bitonic_sort_holes_reg(a, b, lane);
-                scan_hole_chunk(w.clo, w.chi, f, a, b, QCQP_INF, hs, lane);
-            } else {
-                int N2 = 64;
-                while (N2 < nh) N2 <<= 1;
-                for (int i = nh + lane; i < N2; i += 32) w.hx[i] = make_double2(QCQP_INF, QCQP_INF);   // pads are inert
-                __syncwarp();
-                bitonic_sort_holes_smem(w.hx, N2, lane);
-                const int nchunk = (nh + 31) >> 5;
-                double2 cur = w.hx[lane];
-                for (int c = 0; c < nchunk; c++) {
-                    const double2 nxt = w.hx[(c + 1 < (N2 >> 5)) ? ((c + 1) << 5) + lane : lane];
-                    const double nextA = (c + 1 < (N2 >> 5)) ? __shfl_sync(FULL, nxt.x, 0) : QCQP_INF;
-                    scan_hole_chunk(w.clo, w.chi, f, cur.x, cur.y, nextA, hs, lane);
-                    cur = nxt;
-                }
-            }
-        }
-        nC = hs.nC;
-        if (f.mu == 1 && f.H < QCQP_INF) {
-            const bool blocked = __any_sync(FULL, hs.blocked);
-            double st = warp_max(hs.stH);
-            if (f.L > st) st = f.L;
-            if (!blocked) {
-                if (lane == 0) { w.clo[nC] = st; w.chi[nC] = f.H; }
-                nC++;
-            }
-        }
-    }
-    __syncwarp();
-    int found = 0, e = 0;
-    double xv = 0.0;
-    if (lane == 0) found = choose_point(p0, q0, r0, w.clo, w.chi, nC, rng, &xv, &e);
-    __syncwarp();
-    *xout = bcast(xv, 0);
-    *err = bcast_i(e, 0);
-    return bcast_i(found, 0);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// onevar_qcqp, general path: the mk constraint coefficients are in scratch (any mk).
-// ---------------------------------------------------------------------------------------------------------
-struct Scratch {
-    double* p; double* q; double* r; int* rel;
-};
-
-__device__ __forceinline__ int solve_level(const WarpMem& w, const Scratch& sc, int mk, double s, double p0, double q0, double r0, MtRng& rng,
-                                           int lane, double* xout, int* err)
-{
-    *err = 0;
-    *xout = 0.0;
-    Fold f;
-    f.init();
-    int nh = 0;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < mk; base += 32) {
-        const int i = base + lane;
-        bool hole = false;
-        Hole hh;
-        hh.a = hh.b = 0.0;
-        if (i < mk) {
-            const double p = sc.p[i], q = sc.q[i];
-            if (!(p == 0.0 && q == 0.0)) {   // nfs filter of qcqp.py:116,166
-                Ival I[2];
-                const int c = feasible_intervals(p, q, sc.r[i], sc.rel[i], s, I);
-                hole = fold_constraint(f, c, I, &hh);
-            }
-        }
-        // some constraint has no feasible point at this level: the total never reaches m + 1
-        if (__any_sync(FULL, f.nempty > 0)) return 0;
-        const unsigned hb = __ballot_sync(FULL, hole);
-        if (hb) {
-            if (hole) w.hx[nh + __popc(hb & lt)] = make_double2(hh.a, hh.b);
-            nh += __popc(hb);
-        }
-        // long lists (circle packing's r: one interval from each of 20 701 constraints): once the partial intersection of the
-        // singles is empty the final one is too
-        if ((base & 511) == 480 && base + 32 < mk) {
-            const double Lp = warp_max(f.L), Hp = -warp_max(-f.H);
-            if (!(Lp < Hp)) return 0;
-        }
-    }
-    fold_allreduce(f);
-    __syncwarp();
-    return holes_finish(w, f, nh, false, 0.0, 0.0, p0, q0, r0, rng, lane, xout, err);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@
 namespace qcqp {
 
 #ifdef BLK_PROF
-#define STAMP(c, slot) do { if ((c).on) { const long long now__ = clock64(); (c).prof[slot] += now__ - (c).last; (c).last = now__; } } while (0)
+#define STAMP(c, slot) do { if ((c).on) { const long long now__ = clock64(); (c).prof[(c).base + (slot)] += now__ - (c).last; (c).last = now__; } } while (0)
 #else
 #define STAMP(c, slot) do { } while (0)
 #endif
@@ -31,14 +31,18 @@ struct BlkLayout {
     int sc_cap;       // coefficient scratch entries in smem; coordinates with more incidences use the per-restart HBM block
     int fval_smem;    // cached f_j in smem?
     int hcap;         // hole capacity (power of two, >= 64)
+    int act_cap;      // phase 1: capacity of the compacted list of constraints that can still matter in this coordinate's bisection
+    unsigned o_ap, o_aq, o_ar, o_arel;
+    unsigned o_whx, o_wclo, o_wchi, o_wres;   // per-warp hole / piece buffers of the speculative phase-1 probes, and their results
     unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_hx, o_clo, o_chi, o_wfd, o_wfi, o_cmax, o_ccnt, o_redd, o_redi, o_ictl,
         o_dctl;
     unsigned total;
 };
 
 enum { BPH_P1 = 0, BPH_P2 = 1, BPH_DONE = 2 };
-// ictl words: [0],[1] hole counters (by call parity), [2],[3] early-exit flags (by call parity), [4] found, [5] err
-enum { IC_NH = 0, IC_FLAG = 2, IC_FOUND = 4, IC_ERR = 5 };
+// ictl words: [0],[1] hole counters (by call parity), [2],[3] early-exit flags (by call parity), [4] found, [5] err,
+// [6] phase-1 compaction: constraints kept, [7] constraints proven inert
+enum { IC_NH = 0, IC_FLAG = 2, IC_FOUND = 4, IC_ERR = 5, IC_NACT = 6, IC_NINERT = 7 };
 
 struct BlkCtx {
     double* x; double* fval;
@@ -50,7 +54,7 @@ struct BlkCtx {
     int tid, warp, lane;
     int par;                        // call parity of solve_level
 #ifdef BLK_PROF
-    long long* prof; long long last; int on;
+    long long* prof; long long last; int on, base;
 #endif
 };
 
@@ -356,6 +360,127 @@ __device__ __forceinline__ int blk_solve_level(BlkCtx& c, const Scr& sc, int cnt
     return c.ictl[IC_FOUND];
 }
 
+// One phase-1 probe (onevar_qcqp at level s with the zero objective, up to the random draw) by ONE warp over the compacted
+// constraint list, into the warp's own hole / piece buffers: returns the number of feasible pieces, ascending in (clo, chi).
+// Per probe: the kept constraints' feasible sets (lanes over constraints) -> fold of the singles and hulls (warp all-reduce) ->
+// holes into shared memory -> the feasible pieces WITHOUT sorting the holes: with
+//     M_i = max(L, max{b_j : a_j < a_i})   and   tie_i = (another hole starts at a_i),
+// hole i ends a piece [M_i, a_i] iff !tie_i and M_i < a_i < H -- exactly what the scan over the sorted list reports (for an untied
+// hole the holes sorted before it are those with a smaller start; a tied one is never reported, so its M is irrelevant) -- and each
+// lane gets the M and the tie count of its own holes from one pass over the list (independent compares instead of the dependent
+// compare-exchange stages of a sorting network).  Pieces are then ranked by their right end; the piece ending at H comes last
+// (onevar.cuh "HOLE formulation").  Kept out of line so that the CTA-wide kernel keeps its register budget.
+__device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi, const double* ap, const double* aq, const double* ar,
+                                           const int* arel, int n_act, int n_inert, double s, int lane, long long* prof)
+{
+    const unsigned lt = (1u << lane) - 1u;
+#ifdef BLK_PROF
+    long long t_last = clock64();
+#define BSTAMP(slot) do { if (prof) { const long long now__ = clock64(); prof[slot] += now__ - t_last; t_last = now__; } } while (0)
+#else
+#define BSTAMP(slot) do { } while (0)
+#endif
+    // ---- feasible sets at level s ----
+    Fold f;
+    f.init();
+    int nh = 0;
+    for (int base = 0; base < n_act; base += 32) {
+        const int i = base + lane;
+        bool hole = false;
+        Hole hh;
+        hh.a = hh.b = 0.0;
+        if (i < n_act) {
+            Ival I[2];
+            const int c = feasible_intervals<true>(ap[i], aq[i], ar[i], arel[i], s, I);
+            hole = fold_constraint(f, c, I, &hh);
+        }
+        const unsigned hb = __ballot_sync(FULL, hole);
+        if (hole) hx[nh + __popc(hb & lt)] = make_double2(hh.a, hh.b);
+        nh += __popc(hb);
+    }
+    BSTAMP(30);
+    fold_allreduce(f);
+    f.mcnt += n_inert; f.m1 += n_inert;
+    if (f.H == QCQP_INF) f.mu += n_inert;
+    BSTAMP(31);
+    // no feasible point for one constraint, or an empty intersection of the singles and hulls: the total never gets full
+    if (f.nempty > 0 || !(f.L < f.H)) return 0;
+    __syncwarp();
+    // ---- pieces ending at a hole start ----
+    int nC = 0;
+    bool blocked = false;
+    double stH = -QCQP_INF;
+    const int nh32 = (nh + 31) & ~31;
+    for (int ib = 0; ib < nh32; ib += 32) {
+        const int i = ib + lane;
+        double a = QCQP_INF, b = QCQP_INF;
+        if (i < nh) { const double2 t = hx[i]; a = t.x; b = t.y; }
+        // one hole over the whole of (L, H): nothing is left whatever the others do
+        if (__any_sync(FULL, i < nh && a <= f.L && f.H <= b)) { BSTAMP(32); return 0; }
+        double M0 = f.L, M1 = f.L;
+        int eq = 0;
+        int j = 0;
+        for (; j + 1 < nh; j += 2) {
+            const double2 u = hx[j], v = hx[j + 1];
+            if (u.x < a && u.y > M0) M0 = u.y;
+            if (v.x < a && v.y > M1) M1 = v.y;
+            eq += (u.x == a) ? 1 : 0;
+            eq += (v.x == a) ? 1 : 0;
+        }
+        if (j < nh) {
+            const double2 u = hx[j];
+            if (u.x < a && u.y > M0) M0 = u.y;
+            eq += (u.x == a) ? 1 : 0;
+        }
+        const double M = (M1 > M0) ? M1 : M0;
+        const bool valid = (i < nh) && (eq == 1) && (M < a) && (a < f.H);
+        if (a <= f.H && f.H <= b) blocked = true;      // pads: a = +inf, never
+        if (b < f.H && b > stH) stH = b;
+        const unsigned vb = __ballot_sync(FULL, valid);
+        if (vb) {
+            if (ib == 0) {
+                // ascending in a: rank = valid holes of the chunk with a smaller start
+                int rank = 0;
+                for (unsigned mask = vb; mask; mask &= mask - 1) {
+                    const int src = __ffs(mask) - 1;
+                    const double av = __shfl_sync(FULL, a, src);
+                    rank += (av < a) ? 1 : 0;
+                }
+                if (valid) { clo[rank] = M; chi[rank] = a; }
+                nC = __popc(vb);
+                __syncwarp();
+            } else {
+                // later chunks are rare (more than 32 holes): lane 0 inserts their pieces one by one, keeping chi ascending
+                for (unsigned mask = vb; mask; mask &= mask - 1) {
+                    const int src = __ffs(mask) - 1;
+                    const double av = __shfl_sync(FULL, a, src), Mv = __shfl_sync(FULL, M, src);
+                    if (lane == 0) {
+                        int q = nC;
+                        while (q > 0 && chi[q - 1] > av) { clo[q] = clo[q - 1]; chi[q] = chi[q - 1]; q--; }
+                        clo[q] = Mv; chi[q] = av;
+                    }
+                    nC++;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    BSTAMP(32);
+    // ---- the piece ending at H ----
+    if (f.mu == 1 && f.H < QCQP_INF) {
+        blocked = __any_sync(FULL, blocked);
+        double st = warp_max(stH);
+        if (f.L > st) st = f.L;
+        if (!blocked) {
+            if (lane == 0) { clo[nC] = st; chi[nC] = f.H; }
+            nC++;
+        }
+    }
+    __syncwarp();
+    BSTAMP(33);
+    return nC;
+}
+
 // cached f_j(x) from scratch for forms j >= j0 (warps take blocks of 32 forms, same per-form summation as cd.cu's
 // refresh_fvals); returns the max constraint violation.  One copy, called from every sweep boundary.
 template <int T>
@@ -424,6 +549,11 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
     c.dctl = reinterpret_cast<double*>(smem + lay.o_dctl);
     c.par = 0;
     const int tid = c.tid;
+    Scratch act;      // phase 1: the constraints of the current coordinate that are not inert over the whole bisection
+    act.p = reinterpret_cast<double*>(smem + lay.o_ap);
+    act.q = reinterpret_cast<double*>(smem + lay.o_aq);
+    act.r = reinterpret_cast<double*>(smem + lay.o_ar);
+    act.rel = reinterpret_cast<int*>(smem + lay.o_arel);
 
     for (int i = tid; i < n; i += T) c.x[i] = X0[rr * n + i];
     for (int i = tid; i < 624; i += T) mt[i] = rngs[rr].key[i];
@@ -439,8 +569,9 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
     const int strict = (prm.mode == MODE_STRICT) ? 1 : 0;
     const double tol = prm.tol, viol_tol = prm.viol_tol;
 #ifdef BLK_PROF
-    long long prof[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    c.prof = prof; c.on = 0; c.last = 0;
+    long long prof[64];
+    for (int i = 0; i < 64; i++) prof[i] = 0;
+    c.prof = prof; c.on = 0; c.last = 0; c.base = 0;
 #endif
     int phase = BPH_P1;
     int t = 0;                    // sweeps done in the current phase
@@ -500,7 +631,8 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
         blk_load_row0(P, pf1);
         for (int k = 0; k < n && phase != BPH_DONE && !skip; k++) {
 #ifdef BLK_PROF
-            c.on = (phase == BPH_P2 && pb1 - pb0 <= lay.sc_cap); c.last = clock64();
+            c.on = (phase == BPH_P1); c.base = (pb1 - pb0 <= lay.sc_cap) ? 0 : 20; c.last = clock64();
+            if (c.on) prof[60 + (c.base ? 1 : 0)]++;
 #endif
             const PMeta cur0 = pf0, cur1 = pf1;
             const int beg = pb0, end = pb1;
@@ -572,11 +704,105 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
                 if (cz == 0) { st.status = QCQP_RUN_EMPTY_MAX; dead = true; }
                 viol = vmax; new_viol = vmax;
                 ss = -tol; es = viol - viol_tol;
+                STAMP(c, 1);
             } else {
                 st.steps_p2++;
             }
+            // ---- phase 1, compaction.  Every probe level of this coordinate satisfies s >= ss0 = -tol.  A concave constraint
+            //      (p < -1e-4, not an equality) whose discriminant q*q - (4p)(r - ss0) is negative has a negative discriminant at
+            //      every such s too -- r - s, (4p)(r - s) and the difference are each monotone in s under round-to-nearest -- so
+            //      its feasible set is the whole line in every probe: it only counts (mcnt, m1).  What is left (circle packing:
+            //      the circles whose band |dy| < 2r the centre can actually hit, plus the two box constraints) usually fits one
+            //      warp, and warp 0 then runs the whole bisection with the warp-level solver -- no block barrier per probe.
+            bool warp_path = false;
+            int n_act = 0, n_inert = 0;
+            if (in_p1 && !dead && lay.act_cap > 0 && (es - ss > tol) && cnt <= 32 * lay.act_cap) {
+                const double ss0 = ss;
+                int my_inert = 0;
+                for (int base = c.warp * 32; base < cnt; base += T) {
+                    const int i = base + c.lane;
+                    double p = 0.0, q = 0.0, r = 0.0;
+                    int rel = 0;
+                    if (i < cnt) { p = sc.p[i]; q = sc.q[i]; r = sc.r[i]; rel = sc.rj[i] & 3; }
+                    const bool counted = !(p == 0.0 && q == 0.0);
+                    const bool inert = counted && rel != QCQP_RELOP_EQ && p < -IVAL_TOL && (q * q - (4 * p) * (r - ss0) < 0);
+                    const bool keep = counted && !inert;
+                    my_inert += inert ? 1 : 0;
+                    const unsigned kb = __ballot_sync(FULL, keep);
+                    if (kb) {
+                        int pos0 = 0;
+                        if (c.lane == 0) pos0 = atomicAdd((int*)(c.ictl + IC_NACT), __popc(kb));
+                        pos0 = __shfl_sync(FULL, pos0, 0);
+                        const int pos = pos0 + __popc(kb & ((1u << c.lane) - 1u));
+                        if (keep && pos < lay.act_cap) { act.p[pos] = p; act.q[pos] = q; act.r[pos] = r; act.rel[pos] = rel; }
+                    }
+                }
+                my_inert = warp_sum_i(my_inert);
+                if (c.lane == 0 && my_inert) atomicAdd((int*)(c.ictl + IC_NINERT), my_inert);
+                __syncthreads();
+                n_act = c.ictl[IC_NACT]; n_inert = c.ictl[IC_NINERT];
+                warp_path = (n_act <= lay.act_cap);
+                STAMP(c, 2);
+#ifdef BLK_PROF
+                if (c.on) { prof[62] += n_act; prof[63] += warp_path ? 1 : 0; }
+#endif
+            }
+            if (warp_path) {
+                // The reference probes one level at a time (qcqp.py:122-131).  Here warp w evaluates the level the loop reaches after w
+                // infeasible probes -- it replays the same (ss + es) / 2 arithmetic, so the levels are the reference's bit for bit --
+                // and the CTA then walks the chain: the leading infeasible probes are all consumed, the first feasible one draws its
+                // random numbers (thread 0, the reference's order) and discards the speculation behind it.
+#ifdef BLK_PROF
+                long long* bprof = (c.on && c.warp == 0) ? prof + c.base : nullptr;
+#else
+                long long* bprof = nullptr;
+#endif
+                double2* my_hx = reinterpret_cast<double2*>(smem + lay.o_whx) + (size_t)c.warp * lay.act_cap;
+                double* my_clo = reinterpret_cast<double*>(smem + lay.o_wclo) + (size_t)c.warp * (lay.act_cap + 2);
+                double* my_chi = reinterpret_cast<double*>(smem + lay.o_wchi) + (size_t)c.warp * (lay.act_cap + 2);
+                volatile int* wres = reinterpret_cast<volatile int*>(smem + lay.o_wres);
+                while (es - ss > tol) {
+                    double lss = ss, sv = 0.0;
+                    bool node = true;
+                    for (int d = 0; d <= c.warp; d++) {
+                        if (!(es - lss > tol)) { node = false; break; }
+                        sv = (lss + es) / 2;
+                        lss = sv;
+                    }
+                    int r = -1;
+                    if (node) r = blk_warp_probe(my_hx, my_clo, my_chi, act.p, act.q, act.r, act.rel, n_act, n_inert, sv, c.lane, bprof);
+                    if (c.lane == 0) wres[c.warp] = r;
+                    __syncthreads();
+                    int e = 0;
+                    for (int w = 0; w < NW; w++) {
+                        const int rw = wres[w];
+                        if (rw < 0) break;                       // es - ss <= tol at this depth: the reference's loop has ended
+                        const double sl = (ss + es) / 2;
+                        if (rw == 0) { ss = sl; continue; }
+                        if (tid == 0) {
+                            // np.random.uniform(*C[np.random.choice(len(C))])  (utilities.py:266-267)
+                            const double* wl = reinterpret_cast<double*>(smem + lay.o_wclo) + (size_t)w * (lay.act_cap + 2);
+                            const double* wh = reinterpret_cast<double*>(smem + lay.o_wchi) + (size_t)w * (lay.act_cap + 2);
+                            const int idx = rng.choice(rw);
+                            const double lo = wl[idx], hi = wh[idx];
+                            int ee = 0;
+                            double xv = 0.0;
+                            if (is_inf(lo) || is_inf(hi)) ee = QCQP_RUN_UNBOUNDED_UNIFORM;
+                            else xv = rng.uniform(lo, hi);
+                            c.dctl[0] = xv; c.ictl[IC_ERR] = ee;
+                        }
+                        __syncthreads();
+                        e = c.ictl[IC_ERR];
+                        new_xi = c.dctl[0]; new_viol = sl; es = sl;
+                        break;
+                    }
+                    __syncthreads();   // the buffers and wres are free again
+                    if (e) { st.status = e; dead = true; break; }
+                }
+                STAMP(c, 3);
+            }
             bool asked = false;
-            while (!dead) {
+            while (!dead && !warp_path) {
                 double s;
                 if (in_p1) {
                     if (!(es - ss > tol)) break;
@@ -624,6 +850,7 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
                     c.x[k] = new_xi;
                 }
             }
+            if (tid == 0 && in_p1) { c.ictl[IC_NACT] = 0; c.ictl[IC_NINERT] = 0; }
             if (dead) phase = BPH_DONE;
             blk_load_row0(P, pf0);
             blk_load_row0(P, pf1);
@@ -648,7 +875,14 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
         mv_out[rr] = (m > 0) ? final_mv : 0.0;
         if (stats_out) stats_out[rr] = st;
 #ifdef BLK_PROF
-        if (rr == 0) for (int i = 10; i < 20; i++) printf("prof[%d] = %lld (%.0f / p2 step)\n", i, prof[i], (double)prof[i] / (double)(st.steps_p2 > 0 ? st.steps_p2 : 1));
+        if (rr == 0) {
+            printf("centre steps %lld radius steps %lld; kept constraints / centre step %.1f; warp path in %lld steps\n", prof[60], prof[61],
+                   (double)prof[62] / (double)(prof[60] > 0 ? prof[60] : 1), prof[63]);
+            for (int i = 30; i < 35; i++) printf("bisect slot %d: %8.0f cycles / centre step\n", i, (double)prof[i] / (double)(prof[60] > 0 ? prof[60] : 1));
+            for (int i = 0; i < 20; i++)
+                if (prof[i] || prof[20 + i]) printf("slot %2d: centre %8.0f cycles / step   radius %10.0f cycles / step\n", i, (double)prof[i] / (double)(prof[60] > 0 ? prof[60] : 1),
+                                                    (double)prof[20 + i] / (double)(prof[61] > 0 ? prof[61] : 1));
+        }
 #endif
     }
 }
@@ -699,9 +933,21 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     l.o_scq = o; o += blk_align((unsigned)l.sc_cap * 8, 16);
     l.o_scr = o; o += blk_align((unsigned)l.sc_cap * 8, 16);
     l.o_screl = o; o += blk_align((unsigned)l.sc_cap * 4, 16);
-    l.o_hx = o; o += (unsigned)hcap * 16;
-    l.o_clo = o; o += blk_align((unsigned)(hcap + 2) * 8, 16);
-    l.o_chi = o; o += blk_align((unsigned)(hcap + 2) * 8, 16);
+    // hole / piece buffers: the CTA-wide solver's (hcap holes) and, over the same bytes, the per-warp ones of the speculative phase-1
+    // probes (act_cap holes per warp) -- a coordinate step uses one or the other
+    l.act_cap = 128;
+    { const char* e = getenv("QCQP_BLK_WARP"); if (e && atoi(e) == 0) l.act_cap = 0; }   // A/B: every probe by the whole CTA
+    {
+        const unsigned o0 = o;
+        l.o_hx = o; o += (unsigned)hcap * 16;
+        l.o_clo = o; o += blk_align((unsigned)(hcap + 2) * 8, 16);
+        l.o_chi = o; o += blk_align((unsigned)(hcap + 2) * 8, 16);
+        unsigned w = o0;
+        l.o_whx = w; w += (unsigned)(NW * l.act_cap) * 16;
+        l.o_wclo = w; w += (unsigned)(NW * (l.act_cap + 2)) * 8;
+        l.o_wchi = w; w += (unsigned)(NW * (l.act_cap + 2)) * 8;
+        if (w > o) o = w;
+    }
     l.o_wfd = o; o += (unsigned)(2 * NW * 2) * 8;
     l.o_wfi = o; o += (unsigned)(2 * NW * 4) * 4;
     l.o_cmax = o; o += blk_align((unsigned)(hcap / 32) * 8, 16);
@@ -710,6 +956,11 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     l.o_redi = o; o += blk_align((unsigned)NW * 4, 16);
     l.o_ictl = o; o += 32;
     l.o_dctl = o; o += 16;
+    l.o_ap = o; o += (unsigned)l.act_cap * 8;
+    l.o_aq = o; o += (unsigned)l.act_cap * 8;
+    l.o_ar = o; o += (unsigned)l.act_cap * 8;
+    l.o_arel = o; o += blk_align((unsigned)l.act_cap * 4, 16);
+    l.o_wres = o; o += blk_align((unsigned)NW * 4, 16);
     l.total = blk_align(o, 128);
     if (l.total > (unsigned)max_smem_optin(p->device))
         return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: per-restart state exceeds shared memory (too many two-interval constraints on one coordinate)");
@@ -723,9 +974,11 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     double* ws_fval = (double*)p->ws;
     double* ws_scr = (double*)((char*)p->ws + a1);
     int* ws_scrj = (int*)((char*)p->ws + a1 + a2);
-    // more restarts than 4 CTAs per SM can hold: the 64-register build of the 128-thread kernel, 8 CTAs per SM
+    // more restarts than 4 CTAs per SM can hold: the 64-register build of the 128-thread kernel, 8 CTAs per SM -- only when every probe
+    // is CTA-wide (QCQP_BLK_WARP=0): with the speculative phase-1 probes all four warps are busy and the 128-register build wins
+    // (C5, 4096 restarts: 2.5 s against 4.0 s)
     const char* f8 = getenv("QCQP_BLK_CTAS");
-    const bool dense8 = (T == 128) && (f8 ? atoi(f8) == 8 : R > 4 * sms);
+    const bool dense8 = (T == 128) && (f8 ? atoi(f8) == 8 : (R > 4 * sms && l.act_cap == 0));
     if (T == 64) return blk_launch_t<64, 12>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (dense8) return blk_launch_t<128, 8>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (T == 512) return blk_launch_t<512, 1>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);

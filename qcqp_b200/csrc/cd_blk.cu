@@ -377,7 +377,9 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
 #ifdef BLK_PROF
     long long t_last = clock64();
 #define BSTAMP(slot) do { if (prof) { const long long now__ = clock64(); prof[slot] += now__ - t_last; t_last = now__; } } while (0)
+#define BCOUNT(slot, v) do { if (prof) prof[slot] += (v); } while (0)
 #else
+#define BCOUNT(slot, v) do { } while (0)
 #define BSTAMP(slot) do { } while (0)
 #endif
     // ---- feasible sets at level s ----
@@ -404,9 +406,13 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
     if (f.H == QCQP_INF) f.mu += n_inert;
     BSTAMP(31);
     // no feasible point for one constraint, or an empty intersection of the singles and hulls: the total never gets full
-    if (f.nempty > 0 || !(f.L < f.H)) return 0;
+    BCOUNT(45, 1); BCOUNT(46, nh);
+    if (f.nempty > 0 || !(f.L < f.H)) { BCOUNT(47, 1); return 0; }
     __syncwarp();
     // ---- pieces ending at a hole start ----
+    // four inert pads behind the list: the walk below reads the list four holes at a time, one group ahead of its use
+    if (lane < 4) hx[nh + lane] = make_double2(QCQP_INF, QCQP_INF);
+    __syncwarp();
     int nC = 0;
     bool blocked = false;
     double stH = -QCQP_INF;
@@ -416,29 +422,41 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
         double a = QCQP_INF, b = QCQP_INF;
         if (i < nh) { const double2 t = hx[i]; a = t.x; b = t.y; }
         // one hole over the whole of (L, H): nothing is left whatever the others do
-        if (__any_sync(FULL, i < nh && a <= f.L && f.H <= b)) { BSTAMP(32); return 0; }
-        double M0 = f.L, M1 = f.L;
-        int eq = 0;
-        int j = 0;
-        for (; j + 1 < nh; j += 2) {
-            const double2 u = hx[j], v = hx[j + 1];
-            if (u.x < a && u.y > M0) M0 = u.y;
-            if (v.x < a && v.y > M1) M1 = v.y;
-            eq += (u.x == a) ? 1 : 0;
-            eq += (v.x == a) ? 1 : 0;
+        if (__any_sync(FULL, i < nh && a <= f.L && f.H <= b)) { BSTAMP(32); BCOUNT(48, 1); return 0; }
+        // M = max(L, max{b_j : a_j < a}) for my hole: one pass over the list (pads: a_j = +inf is never smaller)
+        double M = f.L;
+        {
+            double2 n0 = hx[0], n1 = hx[1], n2 = hx[2], n3 = hx[3];
+#pragma unroll 1
+            for (int j = 0; j < nh; j += 4) {
+                const double2 u0 = n0, u1 = n1, u2 = n2, u3 = n3;
+                if (j + 4 < nh) { n0 = hx[j + 4]; n1 = hx[j + 5]; n2 = hx[j + 6]; n3 = hx[j + 7]; }
+                if (u0.x < a && u0.y > M) M = u0.y;
+                if (u1.x < a && u1.y > M) M = u1.y;
+                if (u2.x < a && u2.y > M) M = u2.y;
+                if (u3.x < a && u3.y > M) M = u3.y;
+            }
         }
-        if (j < nh) {
-            const double2 u = hx[j];
-            if (u.x < a && u.y > M0) M0 = u.y;
-            eq += (u.x == a) ? 1 : 0;
-        }
-        const double M = (M1 > M0) ? M1 : M0;
-        const bool valid = (i < nh) && (eq == 1) && (M < a) && (a < f.H);
+        const bool valid0 = (i < nh) && (M < a) && (a < f.H);
         if (a <= f.H && f.H <= b) blocked = true;      // pads: a = +inf, never
         if (b < f.H && b > stH) stH = b;
-        const unsigned vb = __ballot_sync(FULL, valid);
-        if (vb) {
-            if (ib == 0) {
+        const unsigned vb0 = __ballot_sync(FULL, valid0);
+        if (vb0) {
+            // a hole whose start another hole shares ends no piece (the reference's dict nets the two events to -2)
+            int ties = 0;
+            if (nh <= 32) {
+                for (unsigned mask = vb0; mask; mask &= mask - 1) {
+                    const int src = __ffs(mask) - 1;
+                    const double av = __shfl_sync(FULL, a, src);
+                    const int t = __popc(__ballot_sync(FULL, a == av));
+                    if (lane == src) ties = t;
+                }
+            } else {
+                for (int j = 0; j < nh; j++) ties += (hx[j].x == a) ? 1 : 0;
+            }
+            const bool valid = valid0 && ties == 1;
+            const unsigned vb = __ballot_sync(FULL, valid);
+            if (vb && ib == 0) {
                 // ascending in a: rank = valid holes of the chunk with a smaller start
                 int rank = 0;
                 for (unsigned mask = vb; mask; mask &= mask - 1) {
@@ -449,7 +467,7 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
                 if (valid) { clo[rank] = M; chi[rank] = a; }
                 nC = __popc(vb);
                 __syncwarp();
-            } else {
+            } else if (vb) {
                 // later chunks are rare (more than 32 holes): lane 0 inserts their pieces one by one, keeping chi ascending
                 for (unsigned mask = vb; mask; mask &= mask - 1) {
                     const int src = __ffs(mask) - 1;
@@ -478,6 +496,7 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
     }
     __syncwarp();
     BSTAMP(33);
+    BCOUNT(51, nC > 0 ? 1 : 0);
     return nC;
 }
 
@@ -757,7 +776,7 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
 #else
                 long long* bprof = nullptr;
 #endif
-                double2* my_hx = reinterpret_cast<double2*>(smem + lay.o_whx) + (size_t)c.warp * lay.act_cap;
+                double2* my_hx = reinterpret_cast<double2*>(smem + lay.o_whx) + (size_t)c.warp * (lay.act_cap + 4);
                 double* my_clo = reinterpret_cast<double*>(smem + lay.o_wclo) + (size_t)c.warp * (lay.act_cap + 2);
                 double* my_chi = reinterpret_cast<double*>(smem + lay.o_wchi) + (size_t)c.warp * (lay.act_cap + 2);
                 volatile int* wres = reinterpret_cast<volatile int*>(smem + lay.o_wres);
@@ -878,6 +897,10 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
         if (rr == 0) {
             printf("centre steps %lld radius steps %lld; kept constraints / centre step %.1f; warp path in %lld steps\n", prof[60], prof[61],
                    (double)prof[62] / (double)(prof[60] > 0 ? prof[60] : 1), prof[63]);
+            printf("warp-0 probes %lld (%.1f / centre step): holes / probe %.1f; empty box %lld, one hole covers %lld, chunks without a start inside the box %lld, "
+                   "starts inside the box / chunk %.2f, feasible %lld\n", prof[45], (double)prof[45] / (double)(prof[60] > 0 ? prof[60] : 1),
+                   (double)prof[46] / (double)(prof[45] > 0 ? prof[45] : 1), prof[47], prof[48], prof[49],
+                   (double)prof[50] / (double)(prof[45] - prof[47] - prof[48] > 0 ? prof[45] - prof[47] - prof[48] : 1), prof[51]);
             for (int i = 30; i < 35; i++) printf("bisect slot %d: %8.0f cycles / centre step\n", i, (double)prof[i] / (double)(prof[60] > 0 ? prof[60] : 1));
             for (int i = 0; i < 20; i++)
                 if (prof[i] || prof[20 + i]) printf("slot %2d: centre %8.0f cycles / step   radius %10.0f cycles / step\n", i, (double)prof[i] / (double)(prof[60] > 0 ? prof[60] : 1),
@@ -943,7 +966,7 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
         l.o_clo = o; o += blk_align((unsigned)(hcap + 2) * 8, 16);
         l.o_chi = o; o += blk_align((unsigned)(hcap + 2) * 8, 16);
         unsigned w = o0;
-        l.o_whx = w; w += (unsigned)(NW * l.act_cap) * 16;
+        l.o_whx = w; w += (unsigned)(NW * (l.act_cap + 4)) * 16;   // + the four pads of blk_warp_probe
         l.o_wclo = w; w += (unsigned)(NW * (l.act_cap + 2)) * 8;
         l.o_wchi = w; w += (unsigned)(NW * (l.act_cap + 2)) * 8;
         if (w > o) o = w;
@@ -979,7 +1002,7 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     // (C5, 4096 restarts: 2.5 s against 4.0 s)
     const char* f8 = getenv("QCQP_BLK_CTAS");
     const bool dense8 = (T == 128) && (f8 ? atoi(f8) == 8 : (R > 4 * sms && l.act_cap == 0));
-    if (T == 64) return blk_launch_t<64, 12>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
+    if (T == 64) return blk_launch_t<64, 8>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (dense8) return blk_launch_t<128, 8>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (T == 512) return blk_launch_t<512, 1>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);
     if (T == 256) return blk_launch_t<256, 2>(p, k, l, dX0, R, drng, dX, df0, dmv, dstats, ws_fval, ws_scr, ws_scrj, stream);

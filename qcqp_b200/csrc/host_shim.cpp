@@ -48,6 +48,18 @@ extern "C" int qcqp_shim_onevar_qcqp(const double* f0 /*p,q,r*/, const double* f
             if (fold_constraint(hf, c, I, &holes[nh])) nh++;
         }
         nC = pieces_from_holes(hf, holes.data(), nh, c_lo.data(), c_hi.data());
+    } else if (force_general == 3) {
+        // the sort-free hole formulation (cd_blk.cu: blk_warp_probe)
+        std::vector<Hole> holes((size_t)m + 1);
+        Fold hf;
+        hf.init();
+        int nh = 0;
+        for (int i = 0; i < m; i++) {
+            Ival I[2];
+            int c = feasible_intervals(fs[3 * i], fs[3 * i + 1], fs[3 * i + 2], relops[i], s, I);
+            if (fold_constraint(hf, c, I, &holes[nh])) nh++;
+        }
+        nC = pieces_from_holes_nosort(hf, holes.data(), nh, c_lo.data(), c_hi.data());
     } else if (ntwo <= 1 && !force_general) {
         nC = sweep_small8(fold, ntwo == 1, T0, T1, c_lo.data(), c_hi.data());   // the kernel's register path
     } else {

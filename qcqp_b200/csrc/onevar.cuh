@@ -17,6 +17,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define QCQP_HD __host__ __device__ __forceinline__
@@ -384,6 +385,41 @@ QCQP_HD int pieces_from_holes(const Fold& f, Hole* h, int nh, double* c_lo, doub
         }
         if (!blocked) { c_lo[nC] = st; c_hi[nC] = f.H; nC++; }
     }
+    return nC;
+}
+
+// The same pieces WITHOUT sorting the holes (scalar statement of cd_blk.cu's blk_warp_probe, held against pieces_from_holes by
+// tests/test_onevar_host.py): with M_i = max(L, max{b_j : a_j < a_i}), hole i ends a piece [M_i, a_i] iff no other hole starts at
+// a_i and M_i < a_i < H.  For an untied hole the holes sorted before it are exactly those with a smaller start; a tied hole is
+// never reported, so the M the sorted scan would give it does not matter.  Pieces are ranked by their right end, the H piece last.
+// One hole over the whole of (L, H) leaves nothing.  The caller has checked nempty == 0.
+QCQP_HD int pieces_from_holes_nosort(const Fold& f, const Hole* h, int nh, double* c_lo, double* c_hi)
+{
+    if (f.mcnt == 0) { c_lo[0] = -QCQP_INF; c_hi[0] = QCQP_INF; return 1; }
+    if (!(f.L < f.H)) return 0;
+    for (int i = 0; i < nh; i++)
+        if (h[i].a <= f.L && f.H <= h[i].b) return 0;
+    int nC = 0;
+    bool blocked = false;
+    double st = f.L;
+    for (int i = 0; i < nh; i++) {
+        const double a = h[i].a, b = h[i].b;
+        if (a <= f.H && f.H <= b) blocked = true;
+        if (b < f.H && b > st) st = b;
+        if (!(a > f.L && a < f.H)) continue;        // M_i >= L: only a start inside (L, H) can end a piece
+        double M = f.L;
+        int eq = 0;
+        for (int j = 0; j < nh; j++) {
+            if (h[j].a < a && h[j].b > M) M = h[j].b;
+            eq += (h[j].a == a) ? 1 : 0;
+        }
+        if (eq != 1 || !(M < a)) continue;
+        int q = nC;
+        while (q > 0 && c_hi[q - 1] > a) { c_lo[q] = c_lo[q - 1]; c_hi[q] = c_hi[q - 1]; q--; }
+        c_lo[q] = M; c_hi[q] = a;
+        nC++;
+    }
+    if (f.mu == 1 && f.H < QCQP_INF && !blocked) { c_lo[nC] = st; c_hi[nC] = f.H; nC++; }
     return nC;
 }
 

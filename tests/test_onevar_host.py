@@ -54,7 +54,7 @@ def test_device_intervals_match_reference(shim, golden):
 
 def test_device_solver_matches_reference_goldens(shim, golden):
     for c in golden["onevar"]:
-        for mode in (0, 1, 2):          # register path, sorted-event path, hole formulation
+        for mode in (0, 1, 2, 3):       # register path, sorted-event path, hole formulation, sort-free holes (cd_blk.cu phase 1)
             st = orc.RngState.from_seed(c["seed"])
             rc, x = _solve(shim, c["f0"], [tuple(f) for f in c["fs"]], c["s"], st, mode)
             if c["error"]:
@@ -97,7 +97,7 @@ def test_device_solver_matches_oracle_random(shim):
             err = False
         except OverflowError:
             err = True
-        for force_general in (0, 1, 2):    # register path (<= 1 two-interval constraint), sorted-event path, hole formulation
+        for force_general in (0, 1, 2, 3):    # register path (<= 1 two-interval constraint), sorted events, holes, sort-free holes
             st_b = orc.RngState.from_seed(t)
             rc, x = _solve(shim, f0, fs, s, st_b, force_general)
             if err:
@@ -183,13 +183,15 @@ def test_hole_formulation_heavy_ties(shim):
             err = False
         except OverflowError:
             err = True
-        st_b = orc.RngState.from_seed(t)
-        rc, x = _solve(shim, f0, fs, s, st_b, 2)
-        if err:
-            assert rc == -2, (t, f0, fs, s)
-            continue
-        if want is None:
-            assert rc == 0, (t, f0, fs, s, x)
-        else:
-            assert rc == 1 and x == want, (t, f0, fs, s, x, want)
-        assert st_a.pos == st_b.pos, (t, f0, fs, s)
+        for mode in (2, 3):                # sorted holes (cd.cu), sort-free holes (cd_blk.cu phase 1)
+            st_b = orc.RngState.from_seed(t)
+            rc, x = _solve(shim, f0, fs, s, st_b, mode)
+            if err:
+                assert rc == -2, (t, f0, fs, s)
+                continue
+            if want is None:
+                assert rc == 0, (mode, t, f0, fs, s, x)
+            else:
+                assert rc == 1 and x == want, (mode, t, f0, fs, s, x, want)
+            assert st_a.pos == st_b.pos, (mode, t, f0, fs, s)
+

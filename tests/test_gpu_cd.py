@@ -262,3 +262,33 @@ def test_cd_blk_default_dispatch_circle_60():
             xo, fo, vo, so, st = out[r]
             assert rng_g[r].pos == st.pos and (sg[r].steps_p1, sg[r].steps_p2) == (so.steps_p1, so.steps_p2)
             assert rel_close(fg[r], fo, rtol=1e-6, atol=1e-9) and rel_close(vg[r], vo, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("gen,gargs,R,kw,randn_start", [
+    ("circle", dict(ncirc=200), 24, dict(num_iters=6), True),                        # C5's instance: 40 of 201 constraints kept per centre coordinate
+    ("circle", dict(ncirc=70), 8, dict(num_iters=8), False),                         # phase 1 reaches feasibility for some restarts, phase 2 follows
+    ("random", dict(n=14, m=220, seed=9, density=0.8), 6, dict(num_iters=6), True),  # > 128 kept constraints on most coordinates: CTA-wide fallback
+    ("random", dict(n=12, m=100, seed=2, density=0.7), 6, dict(num_iters=8), True),  # 33..128 kept, mixed relops: several hole chunks per probe
+])
+def test_cd_blk_warp_probes_equal_cta_wide_probes(gen, gargs, R, kw, randn_start, monkeypatch):
+    """Phase 1 of cd_blk_kernel with the compacted, warp-local, speculative probes (default) against every probe CTA-wide over the full
+    constraint list (QCQP_BLK_WARP=0, the round-1 path that the oracle tests above also hold): identical bits of x, f0, maxviol,
+    statistics and MT19937 position."""
+    from qcqp_b200 import engine
+    forms, _ = GEN[gen](**gargs)
+    n = forms[0][1].size
+    rs = np.random.RandomState(77)
+    X0 = rs.randn(R, n) if randn_start else np.abs(rs.randn(R, n)) * 3 + 0.5
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QCQP_BLK_WARP", mode)
+        pack = engine.Pack(forms)
+        rng = engine.rng_states(seeds=500 + np.arange(R))
+        X, f0, mv, st = pack.cd_improve(X0, rng, strict=4, **kw)
+        out[mode] = (X.copy(), f0.copy(), mv.copy(), [(s.steps_p1, s.steps_p2, s.updates_p1, s.updates_p2, s.sweeps_p1, s.sweeps_p2, s.status, s.steps_skipped) for s in st],
+                     [r.pos for r in rng])
+        pack.close()
+    a, b = out["1"], out["0"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3] == b[3] and a[4] == b[4]
+    assert sum(s[2] for s in a[3]) > 0          # phase 1 did move something

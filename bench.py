@@ -444,22 +444,36 @@ def run_cd_config(env, key, steps, warmup, cpu_leg, light=False):
     else:
         h2d = Ap.nbytes + R * C.sizeof(lib.RngState)
         d2h = R * n * 8 + 2 * R * 8 + R * C.sizeof(lib.CdStats) + R * C.sizeof(lib.RngState)
-    for it in range(1 + (1 if light else min(steps, 3))):
-        env.barrier()
-        t0 = time.perf_counter()
-        if sdr:
-            res = pack.sdr_cd_pipeline(seeds, mu=mu if it == 0 else None, F=F if it == 0 else None, Z=Ap, out=out_e)
-            fh, vh, sth, Xh = res["f0"], res["maxviol"], res["stats"], res["X"]
-        else:
-            rng_e = engine.rng_states(seeds=[int(s) for s in seeds])
-            Xh, fh, vh, sth = pack.cd_improve(Ap, rng_e)
-        b, f, i = local_best(fh, vh)
-        gb = global_best(b, f, lo + i if i >= 0 else -1, device=env.dev, x=Xh[i] if i >= 0 else np.zeros(n))
-        env.barrier()
-        dt = time.perf_counter() - t0
-        if it > 0:
-            e2e_t.append(dt)
-            e2e_sweeps = sum(s.steps_p1 + s.steps_p2 for s in sth) / float(n)
+    # Two passes over the same loop.  single: every call uploads its own inputs first (one isolated request).  pipelined (the steady
+    # state of a caller that runs batch after batch, SDR configurations): before the call on this step's batch the upload of the
+    # NEXT step's standard normals is started with qcqp_sdr_prefetch, so it runs beside this step's kernels; every step still
+    # issues one 8 MB upload from pinned memory and reads its results back inside its timed region.
+    e2e_single = None
+    for mode in (("single", "pipelined") if (sdr and R) else ("single",)):
+        e2e_t = []
+        if mode == "pipelined":
+            pack.sdr_prefetch(Ap)                      # the first step's inputs (untimed warm-up step below consumes them)
+        for it in range(1 + (1 if light else min(steps, 3))):
+            env.barrier()
+            t0 = time.perf_counter()
+            if sdr:
+                if mode == "pipelined":
+                    pack.sdr_prefetch(Ap)              # next step's inputs: asynchronous, overlaps this step's kernels
+                res = pack.sdr_cd_pipeline(seeds, mu=mu if (it == 0 and mode == "single") else None, F=F if (it == 0 and mode == "single") else None,
+                                           Z=Ap, out=out_e)
+                fh, vh, sth, Xh = res["f0"], res["maxviol"], res["stats"], res["X"]
+            else:
+                rng_e = engine.rng_states(seeds=[int(s) for s in seeds])
+                Xh, fh, vh, sth = pack.cd_improve(Ap, rng_e)
+            b, f, i = local_best(fh, vh)
+            gb = global_best(b, f, lo + i if i >= 0 else -1, device=env.dev, x=Xh[i] if i >= 0 else np.zeros(n))
+            env.barrier()
+            dt = time.perf_counter() - t0
+            if it > 0:
+                e2e_t.append(dt)
+                e2e_sweeps = sum(s.steps_p1 + s.steps_p2 for s in sth) / float(n)
+        if mode == "single":
+            e2e_single = env.max_over_ranks([float(np.mean(e2e_t))])[0]
     e2e_time = env.max_over_ranks([float(np.mean(e2e_t))])[0]
     e2e_sweeps = env.sum_over_ranks([e2e_sweeps])[0]
     agree = bool(np.allclose(fh, d_f.cpu().numpy(), rtol=1e-9, atol=0)) if R else True
@@ -516,7 +530,12 @@ def run_cd_config(env, key, steps, warmup, cpu_leg, light=False):
                        "on_box_peaks": peaks, "device_vs_host_api_agree": agree, "wall_s_timed_loop": wall},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_sweeps / e2e_time, "unit": cfg["unit"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_time},
+                    "ms_per_step": 1e3 * e2e_time,
+                    "how": ("steady state of consecutive batches: the upload of the next step's inputs (qcqp_sdr_prefetch, pinned memory) is issued "
+                            "before this step's qcqp_sdr_cd_pipeline call and runs beside its kernels; results read back in the call"
+                            if (sdr and R) else "one host-buffer call per step, copies inside the call"),
+                    "single_call": {"value": e2e_sweeps / e2e_single, "ms_per_step": 1e3 * e2e_single,
+                                    "what": "the same call with nothing overlapped: upload, kernels, read-back in sequence"}},
             # per step: SDR (GEMM, GEMM row-dot, finish) + CD launch sequence + best (+ best over the ranks)
             "gpu_launches": ((3 if sdr else 0) + (5 if parts is not None else 1) + 1 + (1 if env.world > 1 else 0)) * steps,
             "clocks": clocks,

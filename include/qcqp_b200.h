@@ -216,6 +216,12 @@ int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* params, const do
                          const uint32_t* seeds /*[S]*/, double* X0 /*[S][n] or NULL*/, double* f0_draw /*[S] or NULL*/,
                          double* maxviol_draw /*[S] or NULL*/, double* X /*[S][n]*/, double* f0 /*[S]*/, double* maxviol /*[S]*/,
                          qcqp_cd_stats* stats /*[S] or NULL*/, qcqp_rng_state* rng_out /*[S] or NULL*/, int32_t* best_idx /*or NULL*/);
+/* Batch after batch: starts the upload of the standard normals Z [S][n] (pinned host memory, for the copy to be asynchronous) of a
+ * LATER qcqp_sdr_cd_pipeline call on a private stream and returns; issued before the call on the current batch, the copy runs beside
+ * that call's kernels.  The later call recognises Z by its address and S and waits for the copy instead of uploading; any other Z
+ * is uploaded as usual.  Z must stay unchanged until that call returns.  At most two prefetches are outstanding (the third
+ * replaces the first).  No reference counterpart: the reference draws on the host, one sample per suggest() (qcqp.py:394-401). */
+int qcqp_sdr_prefetch(qcqp_pack* pack, const double* Z /*[S][n]*/, int32_t S);
 
 /* ---- best pick: argmin in the QCQPForm.better order (utilities.py:135-146): lexicographic on
  *      (int(maxviol / tol), f0), later index wins exact ties. ---------------------------------------------------- */

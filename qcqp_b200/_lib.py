@@ -78,6 +78,7 @@ EXPORTS = {
                                        C.c_void_p, C.c_void_p]),
     "qcqp_sdr_sample_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcqp_sdr_prefetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "qcqp_sdr_cd_pipeline": (C.c_int, [C.c_void_p, C.POINTER(CdParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),

@@ -304,11 +304,23 @@ extern "C" int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* param
     qcqp_cd_stats* dS = ar.take<qcqp_cd_stats>(S * sizeof(qcqp_cd_stats));
     uint32_t* dSeeds = ar.take<uint32_t>(S * 4);
     int* dBest = ar.take<int>(64);
-    if (Z) QCQP_CUDA_TRY(cudaMemcpyAsync(dZ, Z, S * n * 8, cudaMemcpyHostToDevice, 0));
+    // standard normals: already on the device if qcqp_sdr_prefetch was given this very array (its upload ran beside the previous call)
+    const double* dZuse = dZ;
+    bool prefetched = false;
+    if (Z) {
+        int pick = -1;
+        for (int j = 0; j < 2; j++)
+            if (pack->zpre_src[j] == Z && pack->zpre_S[j] == S && (pick < 0 || pack->zpre_seq[j] < pack->zpre_seq[pick])) pick = j;
+        if (pick >= 0) {
+            QCQP_CUDA_TRY(cudaStreamWaitEvent(0, pack->zpre_ev[pick], 0));
+            dZuse = pack->zpre[pick]; pack->zpre_src[pick] = nullptr; prefetched = true;
+        }
+    }
+    if (Z && !prefetched) QCQP_CUDA_TRY(cudaMemcpyAsync(dZ, Z, S * n * 8, cudaMemcpyHostToDevice, 0));
     QCQP_CUDA_TRY(cudaMemcpyAsync(dSeeds, seeds, S * 4, cudaMemcpyHostToDevice, 0));
     mt_seed_kernel<<<(S + 127) / 128, 128, 0, 0>>>(dSeeds, dR, S);
     QCQP_CUDA_TRY(cudaGetLastError());
-    TRY(sdr_launch(pack, pack->sdr_mu, pack->sdr_F, Z ? dZ : nullptr, seed, S, dX0, dFs, dMs, 0));
+    TRY(sdr_launch(pack, pack->sdr_mu, pack->sdr_F, Z ? dZuse : nullptr, seed, S, dX0, dFs, dMs, 0));
     pack->x_mirror = pinned_alias(X); pack->x_mirror_done = false;
     const int rc_cd = cd_launch(pack, params, dX0, S, dR, dX, dF0, dM, dS, 0);
     const bool delivered = pack->x_mirror_done;
@@ -325,6 +337,29 @@ extern "C" int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* param
     if (rng_out) QCQP_CUDA_TRY(cudaMemcpyAsync(rng_out, dR, S * sizeof(qcqp_rng_state), cudaMemcpyDeviceToHost, 0));
     if (best_idx) QCQP_CUDA_TRY(cudaMemcpyAsync(best_idx, dBest, 4, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    return QCQP_OK;
+}
+
+// Upload of the standard normals of a LATER qcqp_sdr_cd_pipeline call, asynchronous, on a private stream: a caller that runs batch
+// after batch issues it before the call on the current batch, and the copy hides behind that call's kernels.
+extern "C" int qcqp_sdr_prefetch(qcqp_pack* pack, const double* Z, int32_t S)
+{
+    TRY(check_pack(pack, "qcqp_sdr_prefetch"));
+    if (!Z || S <= 0) return fail(QCQP_ERR_INVALID, "qcqp_sdr_prefetch: bad argument");
+    const size_t bytes = (size_t)S * pack->v.n * 8;
+    // an empty slot if there is one, else the older of the two
+    int i = !pack->zpre_src[0] ? 0 : (!pack->zpre_src[1] ? 1 : (pack->zpre_seq[0] < pack->zpre_seq[1] ? 0 : 1));
+    if (!pack->zpre_stream) QCQP_CUDA_TRY(cudaStreamCreateWithFlags(&pack->zpre_stream, cudaStreamNonBlocking));
+    if (!pack->zpre_ev[i]) QCQP_CUDA_TRY(cudaEventCreateWithFlags(&pack->zpre_ev[i], cudaEventDisableTiming));
+    if (pack->zpre_cap[i] < bytes) {
+        if (pack->zpre[i]) QCQP_CUDA_TRY(cudaFree(pack->zpre[i]));
+        pack->zpre[i] = nullptr; pack->zpre_cap[i] = 0; pack->zpre_src[i] = nullptr;
+        QCQP_CUDA_TRY(cudaMalloc((void**)&pack->zpre[i], bytes));
+        pack->zpre_cap[i] = bytes;
+    }
+    QCQP_CUDA_TRY(cudaMemcpyAsync(pack->zpre[i], Z, bytes, cudaMemcpyHostToDevice, pack->zpre_stream));
+    QCQP_CUDA_TRY(cudaEventRecord(pack->zpre_ev[i], pack->zpre_stream));
+    pack->zpre_src[i] = Z; pack->zpre_S[i] = S; pack->zpre_seq[i] = ++pack->zpre_count;
     return QCQP_OK;
 }
 

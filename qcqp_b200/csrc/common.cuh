@@ -133,6 +133,17 @@ struct qcqp_pack {
     // overlaps the tail of the launch instead of following it.
     double* x_mirror;
     bool x_mirror_done;
+    // qcqp_sdr_prefetch: two device staging buffers for the standard normals of FUTURE qcqp_sdr_cd_pipeline calls, filled on a private
+    // non-blocking stream while the current call computes; a pipeline call whose Z pointer matches a filled slot waits for that slot's
+    // event instead of uploading
+    double* zpre[2];
+    size_t zpre_cap[2];
+    const double* zpre_src[2];
+    int zpre_S[2];
+    unsigned long long zpre_seq[2], zpre_count;   // order of the prefetches: a call takes the OLDEST slot that matches
+    cudaEvent_t zpre_ev[2];
+    cudaStream_t zpre_stream;
+    int zpre_next;
 };
 
 namespace qcqp {

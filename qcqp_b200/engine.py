@@ -207,6 +207,13 @@ class Pack:
         return X, f0, mv
 
 
+    def sdr_prefetch(self, Z):
+        """Starts the upload of the standard normals of a LATER sdr_cd_pipeline(Z=Z) call (same array object, pinned for the copy to
+        be asynchronous) and returns: issued before the call on the current batch, the copy hides behind that call's kernels."""
+        if not (isinstance(Z, np.ndarray) and Z.dtype == np.float64 and Z.flags["C_CONTIGUOUS"]):
+            raise Exception("sdr_prefetch needs the C-contiguous float64 array that will be passed to sdr_cd_pipeline")
+        check(_lib.load().qcqp_sdr_prefetch(self._h, _ptr(Z), int(Z.size // self.n)))
+
     def sdr_cd_pipeline(self, seeds, mu=None, F=None, Z=None, S=None, seed=0, want_draws=False, want_rng=False, out=None,
                         num_iters=1000, viol_tol=1e-2, tol=1e-4, phase1=True, strict=False, refresh_every=0):
         """S draws x_s = mu + z_s F (qcqp.py:394-401), improve_coord_descent of every draw with the stream of

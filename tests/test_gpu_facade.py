@@ -168,6 +168,39 @@ def test_pinned_result_array_is_filled_by_the_kernel():
     pack.close()
 
 
+def test_prefetched_standard_normals_give_the_same_run():
+    """qcqp_sdr_prefetch: the standard normals of a later pipeline call uploaded ahead on a private stream.  The call that gets the very
+    same (pinned) array consumes the prefetched copy -- oldest first when the same array was prefetched twice -- and returns the bytes
+    of the plain call; a call with another array, or another S, ignores the prefetch and uploads as usual."""
+    import torch
+    from qcqp_b200 import engine, problems as pb
+    n, S = 100, 96
+    forms, _ = pb.boolean_least_squares(n, 150, seed=3)
+    pack = engine.Pack(forms)
+    mu, _Sg, F = engine.sdr_factor(pb.synthetic_sdr_solution(n, rank=5, seed=2))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    Za, Zb = pin(np.random.RandomState(8).standard_normal((S, n))), pin(np.random.RandomState(9).standard_normal((S, n)))
+    seeds = 500 + np.arange(S)
+    ref_a = pack.sdr_cd_pipeline(seeds, mu=mu, F=F, Z=Za)
+    ref_b = pack.sdr_cd_pipeline(seeds, Z=Zb)
+    assert not np.array_equal(ref_a["X"], ref_b["X"])
+    same = lambda r, q: np.array_equal(r["X"], q["X"]) and np.array_equal(r["f0"], q["f0"]) and np.array_equal(r["maxviol"], q["maxviol"]) and r["best"] == q["best"]
+    # batch after batch: prefetch B, run A (plain upload), run B (prefetched), prefetch A twice, run A twice
+    pack.sdr_prefetch(Zb)
+    assert same(pack.sdr_cd_pipeline(seeds, Z=Za), ref_a)
+    assert same(pack.sdr_cd_pipeline(seeds, Z=Zb), ref_b)
+    pack.sdr_prefetch(Za); pack.sdr_prefetch(Za)
+    assert same(pack.sdr_cd_pipeline(seeds, Z=Za), ref_a)
+    assert same(pack.sdr_cd_pipeline(seeds, Z=Za), ref_a)
+    # a prefetch nobody consumes, then a call with fewer draws of the same array: not a match, plain upload of its own rows
+    pack.sdr_prefetch(Zb)
+    half = pack.sdr_cd_pipeline(seeds[:64], Z=Zb[:64])
+    assert np.array_equal(half["X"], ref_b["X"][:64])
+    with pytest.raises(Exception):
+        pack.sdr_prefetch(Zb[:, ::2])                 # not the contiguous array a pipeline call would receive
+    pack.close()
+
+
 def test_reserved_pack_runs_under_cuda_graph_capture():
     """After qcqp_pack_reserve the `_device` entry points only enqueue work: the whole step (SDR draws -> coordinate descent ->
     best pick) is captured into a CUDA graph on a side stream and replayed; same bytes as the eager calls."""

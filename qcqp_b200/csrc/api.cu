@@ -299,11 +299,21 @@ extern "C" int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* param
     Arena ar; ar.base = (char*)pack->io;
     double* dZ = ar.take<double>(S * n * 8); double* dX0 = ar.take<double>(S * n * 8); double* dX = ar.take<double>(S * n * 8);
     double* dFs = ar.take<double>(S * 8); double* dMs = ar.take<double>(S * 8);
-    double* dF0 = ar.take<double>(S * 8); double* dM = ar.take<double>(S * 8);
     qcqp_rng_state* dR = ar.take<qcqp_rng_state>(S * sizeof(qcqp_rng_state));
-    qcqp_cd_stats* dS = ar.take<qcqp_cd_stats>(S * sizeof(qcqp_cd_stats));
     uint32_t* dSeeds = ar.take<uint32_t>(S * 4);
+    // the small results lie back to back: ONE read-back into the pack's pinned staging block, then host copies (instead of four
+    // staged copies into the caller's possibly pageable arrays)
+    const size_t small0 = ar.off;
+    double* dF0 = ar.take<double>(S * 8); double* dM = ar.take<double>(S * 8);
+    qcqp_cd_stats* dS = ar.take<qcqp_cd_stats>(S * sizeof(qcqp_cd_stats));
     int* dBest = ar.take<int>(64);
+    const size_t small_bytes = ar.off - small0;
+    if (pack->h_small_cap < small_bytes) {
+        if (pack->h_small) QCQP_CUDA_TRY(cudaFreeHost(pack->h_small));
+        pack->h_small = nullptr; pack->h_small_cap = 0;
+        QCQP_CUDA_TRY(cudaHostAlloc(&pack->h_small, small_bytes, cudaHostAllocDefault));
+        pack->h_small_cap = small_bytes;
+    }
     // standard normals: already on the device if qcqp_sdr_prefetch was given this very array (its upload ran beside the previous call)
     const double* dZuse = dZ;
     bool prefetched = false;
@@ -328,15 +338,17 @@ extern "C" int qcqp_sdr_cd_pipeline(qcqp_pack* pack, const qcqp_cd_params* param
     TRY(rc_cd);
     if (best_idx) TRY(best_launch(dF0, dM, S, 1e-4, dBest, nullptr, nullptr, 0));
     if (!delivered) QCQP_CUDA_TRY(cudaMemcpyAsync(X, dX, S * n * 8, cudaMemcpyDeviceToHost, 0));
-    QCQP_CUDA_TRY(cudaMemcpyAsync(f0, dF0, S * 8, cudaMemcpyDeviceToHost, 0));
-    QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol, dM, S * 8, cudaMemcpyDeviceToHost, 0));
+    QCQP_CUDA_TRY(cudaMemcpyAsync(pack->h_small, (char*)pack->io + small0, small_bytes, cudaMemcpyDeviceToHost, 0));
     if (X0) QCQP_CUDA_TRY(cudaMemcpyAsync(X0, dX0, S * n * 8, cudaMemcpyDeviceToHost, 0));
     if (f0_draw) QCQP_CUDA_TRY(cudaMemcpyAsync(f0_draw, dFs, S * 8, cudaMemcpyDeviceToHost, 0));
     if (maxviol_draw) QCQP_CUDA_TRY(cudaMemcpyAsync(maxviol_draw, dMs, S * 8, cudaMemcpyDeviceToHost, 0));
-    if (stats) QCQP_CUDA_TRY(cudaMemcpyAsync(stats, dS, S * sizeof(qcqp_cd_stats), cudaMemcpyDeviceToHost, 0));
     if (rng_out) QCQP_CUDA_TRY(cudaMemcpyAsync(rng_out, dR, S * sizeof(qcqp_rng_state), cudaMemcpyDeviceToHost, 0));
-    if (best_idx) QCQP_CUDA_TRY(cudaMemcpyAsync(best_idx, dBest, 4, cudaMemcpyDeviceToHost, 0));
     QCQP_CUDA_TRY(cudaStreamSynchronize(0));
+    const char* hs = (const char*)pack->h_small;
+    memcpy(f0, hs + ((char*)dF0 - ((char*)pack->io + small0)), S * 8);
+    memcpy(maxviol, hs + ((char*)dM - ((char*)pack->io + small0)), S * 8);
+    if (stats) memcpy(stats, hs + ((char*)dS - ((char*)pack->io + small0)), S * sizeof(qcqp_cd_stats));
+    if (best_idx) memcpy(best_idx, hs + ((char*)dBest - ((char*)pack->io + small0)), 4);
     return QCQP_OK;
 }
 

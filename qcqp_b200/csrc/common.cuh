@@ -144,6 +144,9 @@ struct qcqp_pack {
     cudaEvent_t zpre_ev[2];
     cudaStream_t zpre_stream;
     int zpre_next;
+    // pinned staging block of the host-buffer pipeline's small results (f0, maxviol, statistics, best index): one read-back
+    void* h_small;
+    size_t h_small_cap;
 };
 
 namespace qcqp {

@@ -112,6 +112,7 @@ extern "C" void qcqp_pack_destroy(qcqp_pack* p)
     if (p->sdr_F) cudaFree(p->sdr_F);
     for (int i = 0; i < 2; i++) { if (p->zpre[i]) cudaFree(p->zpre[i]); if (p->zpre_ev[i]) cudaEventDestroy(p->zpre_ev[i]); }
     if (p->zpre_stream) cudaStreamDestroy(p->zpre_stream);
+    if (p->h_small) cudaFreeHost(p->h_small);
     if (p->ev_ok) for (int i = 0; i < 6; i++) cudaEventDestroy(p->ev[i]);
     delete p;
 }
@@ -276,7 +277,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     p->ws = nullptr; p->ws_bytes = 0; p->io = nullptr; p->io_bytes = 0; p->ws2 = nullptr; p->ws2_bytes = 0; p->has_eig = false; p->lpc_ok = false; p->sdr_mu = nullptr; p->sdr_F = nullptr; p->sdr_ok = false;
     p->ev_ok = false; p->ev_count = 0; p->tmap_state = 0; p->d_ctr = nullptr; p->x_mirror = nullptr; p->x_mirror_done = false;
     for (int i = 0; i < 2; i++) { p->zpre[i] = nullptr; p->zpre_cap[i] = 0; p->zpre_src[i] = nullptr; p->zpre_S[i] = 0; p->zpre_ev[i] = nullptr; }
-    p->zpre_stream = nullptr; p->zpre_next = 0; p->zpre_seq[0] = p->zpre_seq[1] = 0; p->zpre_count = 0;
+    p->zpre_stream = nullptr; p->zpre_next = 0; p->zpre_seq[0] = p->zpre_seq[1] = 0; p->zpre_count = 0; p->h_small = nullptr; p->h_small_cap = 0;
     std::memset(&p->lpc, 0, sizeof(p->lpc));
     cudaGetDevice(&p->device);
     p->objective_dense = dense_slot[0] >= 0;

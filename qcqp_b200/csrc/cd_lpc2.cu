@@ -341,12 +341,6 @@ cd_lpc2_kernel(const __grid_constant__ CUtensorMap tmapD, PackView P, LpcView V,
                 // this lane's step as it stands: 0 certainly no move, 1 moves to fxi_me (the endpoint of its region), 2 reference arithmetic
                 int code_me = 2;
                 double fxi_me = 0.0, dl_me = 0.0;
-                // (rlo, rhi): the part of this lane's certified region, four margins inside its thresholds, in which its step stays
-                // what the last classification said.  A move shifts g_k by |P_0[i,k] delta|, small against the width of a region, so
-                // most moves leave every pending lane inside its interval and NOTHING is re-classified: the next mover is the next
-                // bit of the cached masks.  Only when a lane leaves its interval are all of them classified again.  (Lanes that
-                // need the reference arithmetic keep code 2 until then: correct in any state, only slower.)
-                double rlo = QCQP_INF, rhi = -QCQP_INF;
                 auto classify = [&]() {
                     const int reg = (int)(gl < GA) + (int)(gl < GB) + (int)(gl < GM) + (int)(gl < GC) + (int)(gl < GE);
                     const double mu = fma(1e-9, fabs(gl), gsc);
@@ -355,20 +349,15 @@ cd_lpc2_kernel(const __grid_constant__ CUtensorMap tmapD, PackView P, LpcView V,
                     fxi_me = (reg == 0) ? ml0 : ((reg == 2) ? mh0 : ((reg == 3) ? ml1 : mh1));
                     dl_me = fxi_me - xk;
                     code_me = cert ? (int)((wmask >> reg) & 1u) : 2;
-                    // thresholds that bound region `reg` in g_k (descending: +inf > GA > GB > GM > GC > GE > -inf)
-                    const double up = (reg == 0) ? QCQP_INF : ((reg == 2) ? GB : ((reg == 3) ? GM : GE));
-                    const double dn = (reg == 0) ? GA : ((reg == 2) ? GM : ((reg == 3) ? GC : -QCQP_INF));
-                    const double mg = 4.0 * fma(1e-9, fmax(is_inf(up) ? 0.0 : fabs(up), is_inf(dn) ? 0.0 : fabs(dn)), gsc);
-                    rlo = cert ? (is_inf(dn) ? dn : dn + mg) : QCQP_INF;
-                    rhi = cert ? (is_inf(up) ? up : up - mg) : -QCQP_INF;
                 };
                 classify();
                 int cur = 0;            // next coordinate of the pass to resolve
                 int steps32 = 0, upd32 = 0;
                 if (prof) { pt_b = clock64(); pt_pro += pt_b - pt_a; }
-                unsigned m_mv = __ballot_sync(FULL, act && code_me == 1), m_ex = __ballot_sync(FULL, act && code_me == 2);
                 while (cur < B) {
                     if (prof) pt_c = clock64();
+                    const bool pend = act && lane >= cur;
+                    const unsigned m_mv = __ballot_sync(FULL, pend && code_me == 1), m_ex = __ballot_sync(FULL, pend && code_me == 2);
                     const unsigned stop = m_mv | m_ex;
                     const int first = stop ? (__ffs(stop) - 1) : B;
                     const int quiet = first - cur;      // steps that change nothing (qcqp.py:172-176)
@@ -426,18 +415,9 @@ cd_lpc2_kernel(const __grid_constant__ CUtensorMap tmapD, PackView P, LpcView V,
                         uc = 0;
                         // the coordinates still to come see the move through their own entry of column `first`
                         if (lane == first) { moved_me = true; mv_gl = gl; mv_xi = fxi; xg[k] = fxi; }   // a coordinate moves at most once per pass
-                        const bool after = act && lane > first;
-                        if (after) gl = fma(D[first * 32 + lane], delta, gl);     // D[lane][first] = D[first][lane]
-                        const unsigned above = (first >= 31) ? 0u : (FULL << (first + 1));
-                        if (__ballot_sync(FULL, after && code_me != 2 && !(gl > rlo && gl < rhi))) {
-                            classify();
-                            m_mv = __ballot_sync(FULL, after && code_me == 1); m_ex = __ballot_sync(FULL, after && code_me == 2);
-                        } else {
-                            m_mv &= above; m_ex &= above;
-                        }
+                        if (act && lane > first) gl = fma(D[first * 32 + lane], delta, gl);     // D[lane][first] = D[first][lane]
+                        classify();
                     } else {
-                        const unsigned above = (first >= 31) ? 0u : (FULL << (first + 1));
-                        m_mv &= above; m_ex &= above;
                         uc++;
                         if (uc == n) { done = true; break; }
                     }

@@ -181,7 +181,8 @@ def _c5_grid_start(seed, r0=0.30, B=10.0):
 def test_c5_circle_packing_200_circles():
     """C5 at full size (N = 401, 20 701 constraints; the radius has 20 702 incident forms -> the >1024-incidence path of
     cd_blk_kernel) against the oracle: (a) suggest(RANDOM) starts through phase-1 sweeps, (b) feasible starts through phase-2
-    sweeps, both to 1e-6 on (f0, maxviol) with equal step counts and stream positions, and (c) the reference-minted first
+    sweeps, both to 1e-6 on (f0, maxviol) with equal step counts and stream positions, (a') four of the random starts to completion
+    (30-50 phase-1 sweeps each) with equal step, update and sweep counts and stream positions, and (c) the reference-minted first
     phase-1 sweep (tests/golden/golden_large.json: circle200_p1)."""
     import json, os
     from oracle import oracle as orc
@@ -211,6 +212,20 @@ def test_c5_circle_packing_200_circles():
         assert rng_g[r].pos == sr.pos, r
         assert rel_close(f0[r], P.eval(0, xo), rtol=1e-6, atol=1e-9) and rel_close(mv[r], P.max_violation(xo), rtol=1e-6, atol=1e-9), r
         assert rel_close(X[r], xo, rtol=1e-6, atol=1e-8), r
+    # ---- (a') the same starts TO COMPLETION (reference defaults: <= 1000 sweeps; they stall in phase 1 after 30-50 sweeps, ~16 000
+    #      coordinate steps and ~220 000 bisection probes each, and are fast-forwarded): 4 restarts against the oracle ----
+    rng_g = engine.rng_states(seeds=np.arange(4))
+    Xc, fc, vc, sc_ = pack.cd_improve(X0[:4], rng_g)
+    rng_o = (orc.RngState * 4)()
+    for r in range(4):
+        rng_o[r] = orc.RngState.from_seed(r)
+    Xo, fo, vo, so = P.improve_cd_batch(X0[:4], rng_o, fast=True, nthreads=0)
+    for r in range(4):
+        assert (sc_[r].steps_p1, sc_[r].steps_p2, sc_[r].updates_p1, sc_[r].sweeps_p1, sc_[r].steps_skipped) == \
+               (so[r].steps_p1, so[r].steps_p2, so[r].updates_p1, so[r].sweeps_p1, so[r].steps_skipped), r
+        assert sc_[r].sweeps_p1 >= 10 and rng_g[r].pos == rng_o[r].pos, r
+        assert rel_close(fc[r], fo[r], rtol=1e-6, atol=1e-9) and rel_close(vc[r], vo[r], rtol=1e-6, atol=1e-9), r
+        assert rel_close(Xc[r], Xo[r], rtol=1e-6, atol=1e-8), r
     # ---- (b) phase 2 from feasible packings: 3 sweeps, 4 restarts against the oracle ----
     Xf = np.stack([_c5_grid_start(7 + r) for r in range(4)])
     rng_g = engine.rng_states(seeds=100 + np.arange(4))

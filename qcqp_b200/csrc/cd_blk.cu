@@ -393,7 +393,7 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
         hh.a = hh.b = 0.0;
         if (i < n_act) {
             Ival I[2];
-            const int c = feasible_intervals<true>(ap[i], aq[i], ar[i], arel[i], s, I);
+            const int c = feasible_intervals(ap[i], aq[i], ar[i], arel[i], s, I);
             hole = fold_constraint(f, c, I, &hh);
         }
         const unsigned hb = __ballot_sync(FULL, hole);

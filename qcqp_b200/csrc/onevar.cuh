@@ -116,25 +116,7 @@ struct Ival { double lo, hi; };
 
 constexpr double IVAL_TOL = 1e-4;  // the default tol of get_feasible_intervals; the reference never overrides it
 
-// x / d.  P2: when d is a (normal) power of two -- circle packing's 2p = -2 and q = +-1, Boolean problems' 2p = 2 -- the quotient is
-// x times the exactly representable 1/d: both are the correctly rounded value of the same real number, so the bits are those of
-// the IEEE division, without its ~125 cycles.  Any other divisor takes the division.
-template <bool P2>
-QCQP_HD double div_exact(double x, double d)
-{
-#if defined(__CUDA_ARCH__)
-    if (P2) {
-        const int hi = __double2hiint(d), lo = __double2loint(d);
-        const int ex = (hi >> 20) & 0x7ff;
-        if (lo == 0 && (hi & 0x000fffff) == 0 && ex >= 1 && ex <= 2045)
-            return x * __hiloint2double((hi & 0x80000000) | ((2046 - ex) << 20), 0);
-    }
-#endif
-    return x / d;
-}
-
 // {x : p x^2 + q x + rr <= 0}; the '<=' branch of utilities.py:210-231 with s already folded into rr
-template <bool P2 = false>
 QCQP_HD int ivals_le0(double p, double q, double rr, Ival* out)
 {
     // q == 0 (x_k^2 = c constraints: Boolean LS, MAXCUT): -q - rD and -q + rD are exactly -rD and +rD, and IEEE division is
@@ -143,9 +125,9 @@ QCQP_HD int ivals_le0(double p, double q, double rr, Ival* out)
         double D = q * q - (4 * p) * rr;
         if (D >= 0) {
             double rD = sqrt(D), den = 2 * p;
-            if (q == 0.0) { const double h = div_exact<P2>(rD, den); out[0].lo = -h; out[0].hi = h; return 1; }
-            out[0].lo = div_exact<P2>(-q - rD, den);
-            out[0].hi = div_exact<P2>(-q + rD, den);
+            if (q == 0.0) { const double h = rD / den; out[0].lo = -h; out[0].hi = h; return 1; }
+            out[0].lo = (-q - rD) / den;
+            out[0].hi = (-q + rD) / den;
             return 1;
         }
         return 0;
@@ -155,37 +137,36 @@ QCQP_HD int ivals_le0(double p, double q, double rr, Ival* out)
         if (D >= 0) {
             double rD = sqrt(D), den = 2 * p;
             if (q == 0.0) {
-                const double h = div_exact<P2>(rD, den);
+                const double h = rD / den;
                 out[0].lo = -QCQP_INF; out[0].hi = h;
                 out[1].lo = -h; out[1].hi = QCQP_INF;
                 return 2;
             }
-            out[0].lo = -QCQP_INF; out[0].hi = div_exact<P2>(-q + rD, den);
-            out[1].lo = div_exact<P2>(-q - rD, den); out[1].hi = QCQP_INF;
+            out[0].lo = -QCQP_INF; out[0].hi = (-q + rD) / den;
+            out[1].lo = (-q - rD) / den; out[1].hi = QCQP_INF;
             return 2;
         }
         out[0].lo = -QCQP_INF; out[0].hi = QCQP_INF;
         return 1;
     }
-    if (q > IVAL_TOL) { out[0].lo = -QCQP_INF; out[0].hi = div_exact<P2>(0.0 - rr, q); return 1; }
-    if (q < -IVAL_TOL) { out[0].lo = div_exact<P2>(0.0 - rr, q); out[0].hi = QCQP_INF; return 1; }
+    if (q > IVAL_TOL) { out[0].lo = -QCQP_INF; out[0].hi = (0.0 - rr) / q; return 1; }
+    if (q < -IVAL_TOL) { out[0].lo = (0.0 - rr) / q; out[0].hi = QCQP_INF; return 1; }
     out[0].lo = -QCQP_INF; out[0].hi = QCQP_INF;
     return 1;
 }
 
 // get_feasible_intervals(f, s) (utilities.py:198-232); at most two intervals come out
-template <bool P2 = false>
 QCQP_HD int feasible_intervals(double p, double q, double r, int relop, double s, Ival* out)
 {
     if (relop != QCQP_RELOP_EQ) {
         // (r - s) folded: the reference computes q*q - 4*p*(r-s) and (s-r)/q.  (s-r) == -(r-s) exactly in IEEE, and
         // 0.0 - (r-s) reproduces it including the sign of zero.
-        return ivals_le0<P2>(p, q, r - s, out);
+        return ivals_le0(p, q, r - s, out);
     }
     Ival a[2], b[2];
     a[0].lo = a[0].hi = a[1].lo = a[1].hi = b[0].lo = b[0].hi = b[1].lo = b[1].hi = 0.0;
-    const int na = ivals_le0<P2>(p, q, r - s, a);       // f1 = (p, q, r - s) <= 0
-    const int nb = ivals_le0<P2>(-p, -q, -r - s, b);    // f2 = (-p, -q, -r - s) <= 0
+    const int na = ivals_le0(p, q, r - s, a);       // f1 = (p, q, r - s) <= 0
+    const int nb = ivals_le0(-p, -q, -r - s, b);    // f2 = (-p, -q, -r - s) <= 0
     // the reference's double loop over (i, k) in the order (0,0), (0,1), (1,0), (1,1), keeping the first two non-empty
     // intersections -- written with static indices only, so that nothing here lives in local memory on the device
     Ival t[4];

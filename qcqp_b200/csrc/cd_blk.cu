@@ -370,8 +370,13 @@ __device__ __forceinline__ int blk_solve_level(BlkCtx& c, const Scr& sc, int cnt
 // lane gets the M and the tie count of its own holes from one pass over the list (independent compares instead of the dependent
 // compare-exchange stages of a sorting network).  Pieces are then ranked by their right end; the piece ending at H comes last
 // (onevar.cuh "HOLE formulation").  Kept out of line so that the CTA-wide kernel keeps its register budget.
+// *solid_out = 1: the intersection of the feasible sets at this level contains NO open interval -- a constraint with an empty set, an
+// empty box, or the box (L, H) covered by the closed holes: no gap (M_i, a_i) with M_i < a_i < H, ties or not, and a hole over the
+// left neighbourhood of H.  That is a statement about sets, free of the reference's reporting quirks (tied starts, coincident right
+// ends), and every constraint's feasible set only grows with the level (each operation of get_feasible_intervals is monotone in
+// s under round-to-nearest): a solid level certifies that every LOWER level reports no piece either.
 __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi, const double* ap, const double* aq, const double* ar,
-                                           const int* arel, int n_act, int n_inert, double s, int lane, long long* prof)
+                                           const int* arel, int n_act, int n_inert, double s, int lane, long long* prof, int* solid_out)
 {
     const unsigned lt = (1u << lane) - 1u;
 #ifdef BLK_PROF
@@ -407,6 +412,7 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
     BSTAMP(31);
     // no feasible point for one constraint, or an empty intersection of the singles and hulls: the total never gets full
     BCOUNT(45, 1); BCOUNT(46, nh);
+    *solid_out = 1;
     if (f.nempty > 0 || !(f.L < f.H)) { BCOUNT(47, 1); return 0; }
     __syncwarp();
     // ---- pieces ending at a hole start ----
@@ -414,7 +420,7 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
     if (lane < 4) hx[nh + lane] = make_double2(QCQP_INF, QCQP_INF);
     __syncwarp();
     int nC = 0;
-    bool blocked = false;
+    bool blocked = false, gap = false, cov = false;
     double stH = -QCQP_INF;
     const int nh32 = (nh + 31) & ~31;
     for (int ib = 0; ib < nh32; ib += 32) {
@@ -439,9 +445,11 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
         }
         const bool valid0 = (i < nh) && (M < a) && (a < f.H);
         if (a <= f.H && f.H <= b) blocked = true;      // pads: a = +inf, never
+        if (a < f.H && f.H <= b) cov = true;
         if (b < f.H && b > stH) stH = b;
         const unsigned vb0 = __ballot_sync(FULL, valid0);
         if (vb0) {
+            gap = true;
             // a hole whose start another hole shares ends no piece (the reference's dict nets the two events to -2)
             int ties = 0;
             if (nh <= 32) {
@@ -497,6 +505,7 @@ __device__ __noinline__ int blk_warp_probe(double2* hx, double* clo, double* chi
     __syncwarp();
     BSTAMP(33);
     BCOUNT(51, nC > 0 ? 1 : 0);
+    *solid_out = (!gap && __any_sync(FULL, cov)) ? 1 : 0;
     return nC;
 }
 
@@ -767,10 +776,16 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
 #endif
             }
             if (warp_path) {
-                // The reference probes one level at a time (qcqp.py:122-131).  Here warp w evaluates the level the loop reaches after w
-                // infeasible probes -- it replays the same (ss + es) / 2 arithmetic, so the levels are the reference's bit for bit --
-                // and the CTA then walks the chain: the leading infeasible probes are all consumed, the first feasible one draws its
-                // random numbers (thread 0, the reference's order) and discards the speculation behind it.
+                // The reference probes one level at a time (qcqp.py:122-131): s = (ss + es) / 2, infeasible -> ss = s, feasible -> es = s.
+                // While its probes are infeasible ss climbs the chain c_1 = (ss + es) / 2, c_{m+1} = (c_m + es) / 2 (K levels until
+                // es - c_K <= tol).  A level that is SOLID (blk_warp_probe: the feasible sets share no open interval) certifies every
+                // lower level infeasible, so the loop's next feasible-or-quirky probe is the first non-solid level of the chain, found
+                // by a search over the chain index: each round the CTA's warps probe up to NW levels spread over the open index range
+                // (always including the deepest one, so a coordinate that cannot move -- 4 of 5 on circle packing -- costs ONE round
+                // instead of 14 probes).  The exact result of the first non-solid level (its pieces stay in the buffers of the warp
+                // that probed it, which sits out the rest of the search) then plays the reference's step: feasible -> thread 0
+                // draws (the reference's stream order) and es drops to it; not feasible (a piece hidden by the reference's tie
+                // rules) -> ss rises to it.  The levels are replayed with the reference's own arithmetic, bit for bit.
 #ifdef BLK_PROF
                 long long* bprof = (c.on && c.warp == 0) ? prof + c.base : nullptr;
 #else
@@ -779,43 +794,65 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
                 double2* my_hx = reinterpret_cast<double2*>(smem + lay.o_whx) + (size_t)c.warp * (lay.act_cap + 4);
                 double* my_clo = reinterpret_cast<double*>(smem + lay.o_wclo) + (size_t)c.warp * (lay.act_cap + 2);
                 double* my_chi = reinterpret_cast<double*>(smem + lay.o_wchi) + (size_t)c.warp * (lay.act_cap + 2);
-                volatile int* wres = reinterpret_cast<volatile int*>(smem + lay.o_wres);
+                volatile int* wres = reinterpret_cast<volatile int*>(smem + lay.o_wres);     // [2 parities][result, index][NW]
+                int rpar = 0;
                 while (es - ss > tol) {
-                    double lss = ss, sv = 0.0;
-                    bool node = true;
-                    for (int d = 0; d <= c.warp; d++) {
-                        if (!(es - lss > tol)) { node = false; break; }
-                        sv = (lss + es) / 2;
-                        lss = sv;
-                    }
-                    int r = -1;
-                    if (node) r = blk_warp_probe(my_hx, my_clo, my_chi, act.p, act.q, act.r, act.rel, n_act, n_inert, sv, c.lane, bprof);
-                    if (c.lane == 0) wres[c.warp] = r;
-                    __syncthreads();
-                    int e = 0;
-                    for (int w = 0; w < NW; w++) {
-                        const int rw = wres[w];
-                        if (rw < 0) break;                       // es - ss <= tol at this depth: the reference's loop has ended
-                        const double sl = (ss + es) / 2;
-                        if (rw == 0) { ss = sl; continue; }
-                        if (tid == 0) {
-                            // np.random.uniform(*C[np.random.choice(len(C))])  (utilities.py:266-267)
-                            const double* wl = reinterpret_cast<double*>(smem + lay.o_wclo) + (size_t)w * (lay.act_cap + 2);
-                            const double* wh = reinterpret_cast<double*>(smem + lay.o_wchi) + (size_t)w * (lay.act_cap + 2);
-                            const int idx = rng.choice(rw);
-                            const double lo = wl[idx], hi = wh[idx];
-                            int ee = 0;
-                            double xv = 0.0;
-                            if (is_inf(lo) || is_inf(hi)) ee = QCQP_RUN_UNBOUNDED_UNIFORM;
-                            else xv = rng.uniform(lo, hi);
-                            c.dctl[0] = xv; c.ictl[IC_ERR] = ee;
+                    int K = 0;
+                    for (double cl = ss; es - cl > tol && K < 4096; K++) cl = (cl + es) / 2;
+                    auto level = [&](int mm) { double cl = ss; for (int i = 0; i < mm; i++) cl = (cl + es) / 2; return cl; };
+                    int lo = 0, hi = K + 1, hi_nC = 0, keep = -1;
+                    while (hi - lo > 1) {
+                        const int span = hi - lo - 1;
+                        const int nev = (keep < 0) ? NW : NW - 1;
+                        const int slot = (keep < 0) ? c.warp : ((c.warp == keep) ? -1 : (c.warp < keep ? c.warp : c.warp - 1));
+                        int mm = -1;
+                        if (slot >= 0) {
+                            if (span <= nev) mm = (slot < span) ? lo + 1 + slot : -1;
+                            else mm = lo + (int)(((long long)(slot + 1) * span + nev - 1) / nev);    // the last slot probes hi - 1
                         }
+                        int r = -1;
+                        if (mm > 0) {
+                            int solid = 0;
+                            const int nC = blk_warp_probe(my_hx, my_clo, my_chi, act.p, act.q, act.r, act.rel, n_act, n_inert, level(mm), c.lane, bprof, &solid);
+                            r = nC | (solid << 30);
+                        }
+                        if (c.lane == 0) { wres[rpar * 2 * NW + c.warp] = r; wres[rpar * 2 * NW + NW + c.warp] = mm; }
                         __syncthreads();
-                        e = c.ictl[IC_ERR];
-                        new_xi = c.dctl[0]; new_viol = sl; es = sl;
-                        break;
+                        for (int w = 0; w < NW; w++) {
+                            const int rw = wres[rpar * 2 * NW + w], mw = wres[rpar * 2 * NW + NW + w];
+                            if (mw <= 0 || rw < 0) continue;
+                            if ((rw >> 30) & 1) { if (mw > lo) lo = mw; }
+                            else if (mw < hi) { hi = mw; hi_nC = rw & 0x3fffffff; keep = w; }
+                        }
+                        // a solid level above a non-solid one: the certificate wins (everything up to lo is infeasible)
+                        if (hi <= lo) { hi = K + 1; hi_nC = 0; keep = -1; }
+                        rpar ^= 1;
                     }
-                    __syncthreads();   // the buffers and wres are free again
+                    const double s_lo = level(lo), s_hi = (hi <= K) ? level(hi) : 0.0;
+                    if (lo >= 1) ss = s_lo;
+                    int e = 0;
+                    if (hi <= K) {
+                        if (hi_nC > 0) {
+                            if (tid == 0) {
+                                // np.random.uniform(*C[np.random.choice(len(C))])  (utilities.py:266-267)
+                                const double* wl = reinterpret_cast<double*>(smem + lay.o_wclo) + (size_t)keep * (lay.act_cap + 2);
+                                const double* wh = reinterpret_cast<double*>(smem + lay.o_wchi) + (size_t)keep * (lay.act_cap + 2);
+                                const int idx = rng.choice(hi_nC);
+                                const double plo = wl[idx], phi = wh[idx];
+                                int ee = 0;
+                                double xv = 0.0;
+                                if (is_inf(plo) || is_inf(phi)) ee = QCQP_RUN_UNBOUNDED_UNIFORM;
+                                else xv = rng.uniform(plo, phi);
+                                c.dctl[0] = xv; c.ictl[IC_ERR] = ee;
+                            }
+                            __syncthreads();
+                            e = c.ictl[IC_ERR];
+                            new_xi = c.dctl[0]; new_viol = s_hi; es = s_hi;
+                            __syncthreads();      // dctl / the piece buffers are free again
+                        } else {
+                            ss = s_hi;
+                        }
+                    }
                     if (e) { st.status = e; dead = true; break; }
                 }
                 STAMP(c, 3);
@@ -983,7 +1020,7 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     l.o_aq = o; o += (unsigned)l.act_cap * 8;
     l.o_ar = o; o += (unsigned)l.act_cap * 8;
     l.o_arel = o; o += blk_align((unsigned)l.act_cap * 4, 16);
-    l.o_wres = o; o += blk_align((unsigned)NW * 4, 16);
+    l.o_wres = o; o += blk_align((unsigned)(4 * NW) * 4, 16);
     l.total = blk_align(o, 128);
     if (l.total > (unsigned)max_smem_optin(p->device))
         return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: per-restart state exceeds shared memory (too many two-interval constraints on one coordinate)");

@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
 #ifdef BLK_PROF
     long long prof[64];
     for (int i = 0; i < 64; i++) prof[i] = 0;
-    c.prof = prof; c.on = 0; c.last = 0; c.base = 0;
+    c.prof = prof; c.on = 0; c.last = 0; c.base = 0; prof[57] = clock64();
 #endif
     int phase = BPH_P1;
     int t = 0;                    // sweeps done in the current phase
@@ -621,7 +621,13 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
             else if (phase == BPH_DONE) what = 5;
         }
         if (what != 0) {
+#ifdef BLK_PROF
+            const long long trf = clock64();
+#endif
             const double mv = blk_refresh_fvals<T>(P, c.x, c.fval, c.redd, (what == 1 || what == 3) ? 1 : 0, strict);
+#ifdef BLK_PROF
+            prof[58] += clock64() - trf; prof[59]++;
+#endif
             const int w = what;
             what = 0;
             if (w == 2) {
@@ -938,6 +944,7 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
                    "starts inside the box / chunk %.2f, feasible %lld\n", prof[45], (double)prof[45] / (double)(prof[60] > 0 ? prof[60] : 1),
                    (double)prof[46] / (double)(prof[45] > 0 ? prof[45] : 1), prof[47], prof[48], prof[49],
                    (double)prof[50] / (double)(prof[45] - prof[47] - prof[48] > 0 ? prof[45] - prof[47] - prof[48] : 1), prof[51]);
+            printf("refresh of the cached f_j: %.0f cycles each, %lld calls; whole kernel %lld cycles\n", (double)prof[58] / (double)(prof[59] > 0 ? prof[59] : 1), prof[59], clock64() - prof[57]);
             for (int i = 30; i < 35; i++) printf("bisect slot %d: %8.0f cycles / centre step\n", i, (double)prof[i] / (double)(prof[60] > 0 ? prof[60] : 1));
             for (int i = 0; i < 20; i++)
                 if (prof[i] || prof[20 + i]) printf("slot %2d: centre %8.0f cycles / step   radius %10.0f cycles / step\n", i, (double)prof[i] / (double)(prof[60] > 0 ? prof[60] : 1),

@@ -42,6 +42,10 @@ constexpr uint32_t INC_FORM_MASK = 0x0fffffffu;
 constexpr int INC_RELOP_SHIFT = 28;
 constexpr uint32_t INC_DENSE_BIT = 0x80000000u;
 
+// one step of f_j(x) = sum_i ((P x)_i + q_i) x_i + r in SciPy's order: y += val * x[col] (col >= 0) or y += val (the q_i entry, col = -1);
+// row >= 0 closes row i: acc += y * x[row], y = 0
+struct EvOp { double val; int col; int row; };
+
 struct PackView {
     int n, m, n_dense, ld;
     int max_inc;     // max incidences of one coordinate
@@ -62,6 +66,10 @@ struct PackView {
     const long long* q_ptr;
     const int* q_idx;
     const double* q_val;
+    // evaluation programs of the sparse forms: the operations of QuadraticFunction.eval in the reference's order, 16 bytes each, so that
+    // a lane streams them with address-independent loads (forms_eval.cuh); ev_ptr[m+2]
+    const long long* ev_ptr;
+    const struct EvOp* ev_op;
     const double* r;
     const int* relop;
     const int* dense_slot;   // [m+1]: slot or -1

@@ -261,6 +261,23 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
         for (int64_t e = d->q_ptr[j]; e < d->q_ptr[j + 1]; e++) { q_idx.push_back(d->q_idx[e]); q_val.push_back(d->q_val[e]); }
         q_ptr[j + 1] = (long long)q_idx.size();
     }
+    // evaluation programs (forms_eval.cuh: eval_sparse_form_seq): rows ascending over the union of P's rows and q's indices; inside a
+    // row P's entries by ascending column, then q_i, then the row is closed
+    std::vector<long long> ev_ptr(nf + 1, 0);
+    std::vector<EvOp> ev_op;
+    for (int j = 0; j < nf; j++) {
+        if (dense_slot[j] < 0) {
+            int64_t e = d->p_ptr[j], pe = d->p_ptr[j + 1], qe = d->q_ptr[j], qend = d->q_ptr[j + 1];
+            while (e < pe || qe < qend) {
+                const int ip = (e < pe) ? d->p_row[e] : 0x7fffffff, iq = (qe < qend) ? d->q_idx[qe] : 0x7fffffff;
+                const int i = ip < iq ? ip : iq;
+                while (e < pe && d->p_row[e] == i) { EvOp o; o.val = d->p_val[e]; o.col = d->p_col[e]; o.row = -1; ev_op.push_back(o); e++; }
+                if (iq == i) { EvOp o; o.val = d->q_val[qe]; o.col = -1; o.row = -1; ev_op.push_back(o); qe++; }
+                ev_op.back().row = i;
+            }
+        }
+        ev_ptr[j + 1] = (long long)ev_op.size();
+    }
     std::vector<double> dense_P((size_t)nd * n * ld, 0.0);
     for (int s = 0; s < nd; s++) {
         int j = dense_form[s];
@@ -294,6 +311,7 @@ extern "C" int qcqp_pack_create(const qcqp_pack_desc* d, qcqp_pack** out)
     UP(inc_rbeg, inc_rbeg); UP(inc_rlen, inc_rlen); UP(row_col, row_col); UP(row_val, row_val);
     UP(f_ptr, f_ptr); UP(f_row, f_row); UP(f_col, f_col); UP(f_val, f_val);
     UP(q_ptr, q_ptr); UP(q_idx, q_idx); UP(q_val, q_val);
+    UP(ev_ptr, ev_ptr); UP(ev_op, ev_op);
     UP(r, r); UP(relop, relop); UP(dense_slot, dense_slot); UP(dense_form, dense_form); UP(dense_P, dense_P);
 #undef UP
     if (rc == QCQP_OK) {

@@ -814,7 +814,8 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
                         int mm = -1;
                         if (slot >= 0) {
                             if (span <= nev) mm = (slot < span) ? lo + 1 + slot : -1;
-                            else mm = lo + (int)(((long long)(slot + 1) * span + nev - 1) / nev);    // the last slot probes hi - 1
+                            else mm = (slot == 0 || nev == 1) ? lo + 1      // the lowest open level (a coordinate that improves is usually feasible there) ...
+                                                                : lo + 1 + (int)(((long long)slot * (span - 1) + nev - 2) / (nev - 1));   // ... the rest spread up to hi - 1
                         }
                         int r = -1;
                         if (mm > 0) {

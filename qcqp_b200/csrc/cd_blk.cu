@@ -11,8 +11,17 @@
 //   shared-memory exchange  ->  holes compacted with one shared-memory atomic per warp  ->  bitonic sort whose stages
 //   with partner distance < the warp's region need only __syncwarp  ->  chunked prefix-max scan, one chunk per warp
 //   ->  thread 0: minimiser + MT19937 draws  ->  every thread updates the cached f_j of its incidences.
+// Phase 1 (the ~14 bisection probes per coordinate of qcqp.py:113-140, the whole of circle packing's default run) does not repeat
+// that CTA-wide probe 14 times:
+//   * constraints proven inert over the whole bisection (concave, negative discriminant at the lowest level) are compacted away;
+//   * a probe over the compact list is WARP-local and sort-free (blk_warp_probe), each warp of the CTA probing another level;
+//   * a "solid" level (the feasible sets share no open interval) certifies every lower level infeasible -- feasible sets only grow
+//     with the level -- so the next non-trivial probe of the reference's loop is found by a search over the chain of levels,
+//     deepest first: a coordinate that cannot move costs one probe round.  Every step is exact; DESIGN.md 4.1.c has the argument.
+// Lists with more than 128 kept constraints (the radius) keep the CTA-wide sequential probes.
 // T is chosen from the number of restarts so that all of them are resident at once (128 registers per thread):
-// T = 512 for R <= 148, 256 for R <= 296, else 128 (4 CTAs per SM; beyond 592 restarts a 64-register build with 8 CTAs per SM).
+// T = 512 for R <= 148, 256 for R <= 296, else 128 (4 CTAs per SM; the 64-register build with 8 CTAs per SM only when every probe is
+// CTA-wide, QCQP_BLK_WARP=0).
 #include "cd_holes.cuh"
 #include "cd_shared.cuh"
 #include "common.cuh"

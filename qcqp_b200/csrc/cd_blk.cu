@@ -42,7 +42,7 @@ struct BlkLayout {
     int hcap;         // hole capacity (power of two, >= 64)
     int act_cap;      // phase 1: capacity of the compacted list of constraints that can still matter in this coordinate's bisection
     unsigned o_ap, o_aq, o_ar, o_arel;
-    unsigned o_whx, o_wclo, o_wchi, o_wres;   // per-warp hole / piece buffers of the speculative phase-1 probes, and their results
+    unsigned o_whx, o_wclo, o_wchi, o_wres, o_wlev;   // per-warp hole / piece buffers of the speculative phase-1 probes, and their results
     unsigned o_x, o_fval, o_mt, o_scp, o_scq, o_scr, o_screl, o_hx, o_clo, o_chi, o_wfd, o_wfi, o_cmax, o_ccnt, o_redd, o_redi, o_ictl,
         o_dctl;
     unsigned total;
@@ -810,11 +810,24 @@ __global__ void __launch_bounds__(T, MINB) cd_blk_kernel(const __grid_constant__
                 double* my_clo = reinterpret_cast<double*>(smem + lay.o_wclo) + (size_t)c.warp * (lay.act_cap + 2);
                 double* my_chi = reinterpret_cast<double*>(smem + lay.o_wchi) + (size_t)c.warp * (lay.act_cap + 2);
                 volatile int* wres = reinterpret_cast<volatile int*>(smem + lay.o_wres);     // [2 parities][result, index][NW]
+                double* my_lev = reinterpret_cast<double*>(smem + lay.o_wlev) + (size_t)c.warp * 64;
                 int rpar = 0;
                 while (es - ss > tol) {
+                    // the chain, once per bracket: every warp keeps its own copy of c_0 = ss, c_1 .. c_K (the first 63; beyond, replayed)
                     int K = 0;
-                    for (double cl = ss; es - cl > tol && K < 4096; K++) cl = (cl + es) / 2;
-                    auto level = [&](int mm) { double cl = ss; for (int i = 0; i < mm; i++) cl = (cl + es) / 2; return cl; };
+                    {
+                        double cl = ss;
+                        __syncwarp();                       // the previous chain's levels have been read by every lane
+                        if (c.lane == 0) my_lev[0] = cl;
+                        for (; es - cl > tol && K < 4096; ) { cl = (cl + es) / 2; K++; if (c.lane == 0 && K < 64) my_lev[K] = cl; }
+                        __syncwarp();
+                    }
+                    auto level = [&](int mm) {
+                        if (mm < 64) return my_lev[mm];
+                        double cl = ss;
+                        for (int i = 0; i < mm; i++) cl = (cl + es) / 2;
+                        return cl;
+                    };
                     int lo = 0, hi = K + 1, hi_nC = 0, keep = -1;
                     while (hi - lo > 1) {
                         const int span = hi - lo - 1;
@@ -1038,6 +1051,7 @@ int blk_launch(qcqp_pack* p, const CdK& k, const double* dX0, int R, qcqp_rng_st
     l.o_ar = o; o += (unsigned)l.act_cap * 8;
     l.o_arel = o; o += blk_align((unsigned)l.act_cap * 4, 16);
     l.o_wres = o; o += blk_align((unsigned)(4 * NW) * 4, 16);
+    l.o_wlev = o; o += (unsigned)(NW * 64) * 8;                  // per warp: the levels of the current chain
     l.total = blk_align(o, 128);
     if (l.total > (unsigned)max_smem_optin(p->device))
         return fail(QCQP_ERR_CAPACITY, "qcqp_cd_improve: per-restart state exceeds shared memory (too many two-interval constraints on one coordinate)");

@@ -115,3 +115,92 @@ extern "C" int qcqp_shim_single_det(const double* f0, const double* f, int32_t r
     }
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Phase-1 bisection of one coordinate (qcqp.py:113-140) with the zero objective, two ways:
+//   mode 0: the reference's loop, one probe per level (hole formulation + choose_point);
+//   mode 1: cd_blk.cu's search -- the chain c_1 = (ss + es) / 2, c_{m+1} = (c_m + es) / 2; a SOLID level certifies every lower level
+//           infeasible, so only the first non-solid level of the chain is probed for real; `nw` levels are examined per round, spread
+//           over the open index range (lowest and deepest included), as the CTA's warps do.
+// out[0..3] = new_xi, new_viol, ss, es at the end; returns the number of levels examined (mode 1) / probes (mode 0), < 0 on error.
+// tests/test_onevar_host.py holds the two against each other (results and MT19937 position) on random and tie-heavy constraint sets.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct ProbeOut { int nC; bool solid; std::vector<double> lo, hi; };
+ProbeOut probe_level(const double* fs, const int32_t* relops, int m, double s)
+{
+    ProbeOut o;
+    std::vector<Hole> holes((size_t)m + 1);
+    Fold f;
+    f.init();
+    int nh = 0;
+    for (int i = 0; i < m; i++) {
+        Ival I[2];
+        const int c = feasible_intervals(fs[3 * i], fs[3 * i + 1], fs[3 * i + 2], relops[i], s, I);
+        if (fold_constraint(f, c, I, &holes[nh])) nh++;
+    }
+    o.lo.assign((size_t)m + 4, 0.0); o.hi.assign((size_t)m + 4, 0.0);
+    o.nC = (f.nempty > 0) ? 0 : pieces_from_holes_nosort(f, holes.data(), nh, o.lo.data(), o.hi.data());
+    o.solid = level_is_solid(f, holes.data(), nh);
+    return o;
+}
+}  // namespace
+
+extern "C" int qcqp_shim_phase1_bisect(const double* fs /*[m][3]*/, const int32_t* relops, int32_t m, double ss, double es, double tol,
+                                       qcqp_rng_state* st, int32_t mode, int32_t nw, double* out4)
+{
+    MtRng rng{st->key, st->pos};
+    double new_xi = 0.0, new_viol = es;
+    int work = 0;
+    auto draw = [&](const ProbeOut& o, double* x) {
+        const int idx = rng.choice(o.nC);
+        if (is_inf(o.lo[idx]) || is_inf(o.hi[idx])) return false;
+        *x = rng.uniform(o.lo[idx], o.hi[idx]);
+        return true;
+    };
+    if (mode == 0) {
+        while (es - ss > tol) {
+            const double s = (ss + es) / 2;
+            const ProbeOut o = probe_level(fs, relops, m, s);
+            work++;
+            if (o.nC == 0) ss = s;
+            else { double x; if (!draw(o, &x)) { st->pos = rng.pos; return -2; } new_xi = x; new_viol = s; es = s; }
+        }
+    } else {
+        while (es - ss > tol) {
+            std::vector<double> lev(1, ss);
+            for (double cl = ss; es - cl > tol && lev.size() < 4096;) { cl = (cl + es) / 2; lev.push_back(cl); }
+            const int K = (int)lev.size() - 1;
+            int lo = 0, hi = K + 1, keep = -1;
+            ProbeOut hi_out;
+            while (hi - lo > 1) {
+                const int span = hi - lo - 1, nev = (keep < 0) ? nw : nw - 1;
+                std::vector<int> idx;
+                for (int slot = 0; slot < nev; slot++) {
+                    int mm = -1;
+                    if (span <= nev) mm = (slot < span) ? lo + 1 + slot : -1;
+                    else mm = (slot == 0 || nev == 1) ? lo + 1 : lo + 1 + (int)(((long long)slot * (span - 1) + nev - 2) / (nev - 1));
+                    if (mm > 0) idx.push_back(mm);
+                }
+                int nlo = lo, nhi = hi;
+                for (int mm : idx) {
+                    const ProbeOut o = probe_level(fs, relops, m, lev[(size_t)mm]);
+                    work++;
+                    if (o.solid) { if (mm > nlo) nlo = mm; }
+                    else if (mm < nhi) { nhi = mm; hi_out = o; keep = 0; }
+                }
+                lo = nlo; hi = nhi;
+                if (hi <= lo) { hi = K + 1; keep = -1; hi_out = ProbeOut(); }
+            }
+            const double s_lo = lev[(size_t)lo], s_hi = (hi <= K) ? lev[(size_t)hi] : 0.0;
+            if (lo >= 1) ss = s_lo;
+            if (hi <= K) {
+                if (hi_out.nC > 0) { double x; if (!draw(hi_out, &x)) { st->pos = rng.pos; return -2; } new_xi = x; new_viol = s_hi; es = s_hi; }
+                else ss = s_hi;
+            }
+        }
+    }
+    st->pos = rng.pos;
+    out4[0] = new_xi; out4[1] = new_viol; out4[2] = ss; out4[3] = es;
+    return work;
+}

@@ -404,6 +404,28 @@ QCQP_HD int pieces_from_holes_nosort(const Fold& f, const Hole* h, int nh, doubl
     return nC;
 }
 
+// "Solid" level (scalar statement of the flag blk_warp_probe returns): the feasible sets at this level share NO open interval -- a
+// constraint with an empty set, an empty box, one hole over the whole box, or no gap (M_i, a_i) with M_i < a_i < H (tied starts or
+// not) together with a hole over the left neighbourhood of H.  A statement about the sets, free of the reference's reporting rules
+// (tied starts, coincident right ends); since every constraint's feasible set only grows with the level, a solid level certifies
+// that every LOWER level reports no piece.  f: the fold of all constraints at the level; h: its holes.
+QCQP_HD bool level_is_solid(const Fold& f, const Hole* h, int nh)
+{
+    if (f.mcnt == 0) return false;
+    if (f.nempty > 0 || !(f.L < f.H)) return true;
+    bool cov = false;
+    for (int i = 0; i < nh; i++) {
+        const double a = h[i].a, b = h[i].b;
+        if (a <= f.L && f.H <= b) return true;
+        if (a < f.H && f.H <= b) cov = true;
+        double M = f.L;
+        for (int j = 0; j < nh; j++)
+            if (h[j].a < a && h[j].b > M) M = h[j].b;
+        if (M < a && a < f.H) return false;           // a gap ends at a_i
+    }
+    return cov;                                        // no gap at a hole start: solid iff the stretch below H is covered too
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the minimiser of f0 = (p, q, r) over the pieces (utilities.py:263-288).  Returns 1 and *xout, 0 for None.
 // *err: QCQP_RUN_UNBOUNDED_UNIFORM when the reference would raise OverflowError.

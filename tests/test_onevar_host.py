@@ -24,6 +24,8 @@ def shim():
     L.qcqp_shim_onevar_qcqp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
     L.qcqp_shim_feasible_intervals.restype = C.c_int
     L.qcqp_shim_feasible_intervals.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_void_p]
+    L.qcqp_shim_phase1_bisect.restype = C.c_int
+    L.qcqp_shim_phase1_bisect.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.qcqp_shim_uniform.restype = C.c_double
     L.qcqp_shim_uniform.argtypes = [C.c_void_p, C.c_double, C.c_double]
     L.qcqp_shim_choice.restype = C.c_int
@@ -195,3 +197,73 @@ def test_hole_formulation_heavy_ties(shim):
                 assert rc == 1 and x == want, (mode, t, f0, fs, s, x, want)
             assert st_a.pos == st_b.pos, (mode, t, f0, fs, s)
 
+
+
+def _ref_bisect(fs, ss, es, tol, st):
+    """coord_descent_phase1's inner loop (qcqp.py:122-131) over the oracle's onevar_qcqp with the zero objective."""
+    new_xi, new_viol, probes = 0.0, es, 0
+    while es - ss > tol:
+        s = (ss + es) / 2
+        xi = orc.onevar_qcqp((0.0, 0.0, 0.0), fs, s, st)
+        probes += 1
+        if xi is None:
+            ss = s
+        else:
+            new_xi, new_viol, es = xi, s, s
+    return new_xi, new_viol, ss, es, probes
+
+
+def test_phase1_bisection_by_solid_level_search_equals_the_reference_loop(shim):
+    """cd_blk.cu's phase-1 bisection: instead of one probe per level, a search over the chain of levels in which a SOLID level (no
+    open interval common to the feasible sets) certifies every lower level infeasible.  Scalar model (host_shim.cpp:
+    qcqp_shim_phase1_bisect, the arithmetic of onevar.cuh) against the reference's loop over the oracle: same new_xi, new_viol,
+    bracket and MT19937 position, for 2- and 4-level rounds, on circle-packing-like lists (concave constraints around centres plus
+    a box), random mixed lists with equalities, and lattice lists built to tie (hidden pieces: non-solid levels that report nothing)."""
+    rs = np.random.RandomState(99)
+    tol = 1e-4
+    saved, total, moved, hidden = 0, 0, 0, 0
+    for t in range(1500):
+        kind = t % 3
+        fs = []
+        if kind == 0:        # circle packing, one centre coordinate: -(x - c)^2 + w <= 0 for every other circle, r <= x <= 1 - r
+            rad = abs(rs.randn()) * 0.3 + 0.02
+            for _ in range(int(rs.randint(3, 60))):
+                cx, dy = rs.randn() * 0.7 + 0.5, rs.randn() * 0.6
+                fs.append((-1.0, 2 * cx, 4 * rad * rad - dy * dy - cx * cx, "<="))
+            fs.append((0.0, -1.0, rad, "<=")); fs.append((0.0, 1.0, rad - 1.0, "<="))
+        elif kind == 1:      # mixed random
+            for _ in range(int(rs.randint(1, 25))):
+                p = rs.randn() * (rs.rand() < 0.8); q = rs.randn(); r = rs.randn() - 0.5
+                if p == 0 and q == 0:
+                    q = 1.0
+                fs.append((float(p), float(q), float(r), "==" if rs.rand() < 0.25 else "<="))
+        else:                # lattice coefficients: exact coincidences of endpoints between constraints
+            for _ in range(int(rs.randint(2, 20))):
+                p = float(rs.choice([-2.0, -1.0, -1.0, -0.5, 0.0, 1.0, 2.0])); q = float(rs.randint(-3, 4))
+                r = float(rs.randint(-6, 3)) * float(rs.choice([1.0, 0.5, 0.25]))
+                if p == 0 and q == 0:
+                    q = 1.0
+                fs.append((p, q, r, "==" if rs.rand() < 0.2 else "<="))
+            for _ in range(rs.randint(0, 3)):
+                fs[rs.randint(0, len(fs))] = fs[rs.randint(0, len(fs))]
+        ss, es = -tol, float(rs.choice([0.05, 0.3, 1.0, 2.0, 4.0, 7.0]) * (1.0 if kind == 2 else rs.rand() + 0.05))
+        st_ref = orc.RngState.from_seed(t)
+        try:
+            want = _ref_bisect(fs, ss, es, tol, st_ref)
+        except OverflowError:
+            continue                                  # an unbounded piece: the reference raises (the kernels report it as an error status)
+        fa = np.ascontiguousarray([f[:3] for f in fs], dtype=np.float64).reshape(-1, 3)
+        ra = np.ascontiguousarray([orc.RELOP_CODE[f[3]] for f in fs], dtype=np.int32)
+        for mode, nw in ((0, 1), (1, 2), (1, 4), (1, 8)):
+            st = orc.RngState.from_seed(t)
+            out = np.zeros(4)
+            work = shim.qcqp_shim_phase1_bisect(fa.ctypes.data, ra.ctypes.data, len(fs), ss, es, tol, C.byref(st), mode, nw, out.ctypes.data)
+            assert work >= 0, (t, mode, nw)
+            assert st.pos == st_ref.pos, (t, mode, nw, fs, es)
+            assert out[1] == want[1] and out[2] == want[2] and out[3] == want[3], (t, mode, nw, out, want)
+            if want[1] != es:                         # some level was feasible: the point drawn there
+                assert out[0] == want[0], (t, mode, nw, out, want)
+            if mode == 1 and nw == 4:
+                total += want[4]; saved += want[4] - min(work, want[4]); moved += int(want[1] != es)
+    assert total > 10000 and moved > 300
+    print("reference probes %d, levels the 4-wide search did not have to examine %d, brackets with a feasible level %d" % (total, saved, moved))

@@ -267,3 +267,43 @@ def test_phase1_bisection_by_solid_level_search_equals_the_reference_loop(shim):
                 total += want[4]; saved += want[4] - min(work, want[4]); moved += int(want[1] != es)
     assert total > 10000 and moved > 300
     print("reference probes %d, levels the 4-wide search did not have to examine %d, brackets with a feasible level %d" % (total, saved, moved))
+
+
+def test_feasible_sets_grow_with_the_level(shim):
+    """The lemma under cd_blk.cu's compaction and its solid-level certificate: in floating point, as computed by
+    get_feasible_intervals, the feasible set of a constraint at level s0 is contained in its feasible set at every s1 >= s0 -- for
+    '<=' and '==' constraints, convex, concave, linear and degenerate, including levels one ulp apart and the discriminant's zero.
+    In particular a concave constraint that is the whole line at s0 stays the whole line."""
+    rs = np.random.RandomState(1234)
+    EQ, LE = orc.RELOP_CODE["=="], orc.RELOP_CODE["<="]
+
+    def sets(p, q, r, rel, s):
+        out = np.zeros(4)
+        n = shim.qcqp_shim_feasible_intervals(p, q, r, rel, s, out.ctypes.data)
+        return [(out[2 * i], out[2 * i + 1]) for i in range(n)]
+
+    whole = 0
+    for t in range(40000):
+        k = t % 5
+        if k == 0:
+            p, q, r = float(rs.choice([-2, -1, -0.5, 0.5, 1, 4])), float(rs.randint(-3, 4)), float(rs.randint(-6, 3)) * 0.5
+        elif k == 1:
+            p, q, r = rs.randn(), rs.randn(), rs.randn()
+        elif k == 2:
+            p, q, r = 0.0, float(rs.choice([-2.0, -1.0, 1.0, 0.5, 3.0])) * (1 if t % 2 else rs.rand() + 0.1), rs.randn()
+        elif k == 3:
+            p, q = float(rs.choice([-1.0, 1.0, -2.0, 0.7])), float(rs.randint(-4, 5))
+            r = q * q / (4 * p) + float(rs.choice([0.0, 1e-16, -1e-16, 1e-9, -1e-9, 1e-3]))     # discriminant at / next to zero
+        else:
+            p, q, r = rs.randn() * 1e-4, rs.randn() * 1e-4, rs.randn()                            # around the 1e-4 classification tolerance
+        rel = EQ if t % 7 == 0 else LE
+        s0 = float(rs.choice([-1e-4, 0.0, 1e-4, 0.3, 1.0])) if t % 3 else float(rs.randn())
+        ds = float(rs.choice([0.0, 1e-4, 0.1, 2.0])) if t % 4 else float(np.spacing(abs(s0)) * rs.randint(0, 4))
+        s1 = s0 + ds
+        A, B = sets(p, q, r, rel, s0), sets(p, q, r, rel, s1)
+        for lo, hi in A:                               # every interval of the lower level lies inside one interval of the higher level
+            assert any(blo <= lo and hi <= bhi for blo, bhi in B), (p, q, r, rel, s0, s1, A, B)
+        if rel == LE and p < -1e-4 and A == [(-np.inf, np.inf)]:
+            whole += 1
+            assert B == [(-np.inf, np.inf)], (p, q, r, s0, s1)
+    assert whole > 500
